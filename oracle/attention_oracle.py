@@ -1,0 +1,259 @@
+"""CPU oracle for the fused-attention hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain PyTorch fp32 on the host CPU, the math that the
+reference's attention kernels implement.  It is the checker for the CUDA path:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.  Nothing under ``flash_attention_b200/``
+imports it and the product path raises if the CUDA library is missing.
+
+Parity pinning: ``oracle/make_golden.py`` runs the reference's own
+``attention_ref`` (extracted from ``/root/reference/tests/test_flash_attn.py:217-304``
+in the build container) on seeded inputs and stores the outputs under
+``tests/golden/``; ``tests/test_oracle_golden.py`` checks this restatement against
+those fixtures.  => parity is PINNED.
+
+What is restated (reference file:line):
+  * score/mask/softmax/PV pipeline        tests/test_flash_attn.py:217-304
+  * bottom-right aligned causal / window  tests/test_flash_attn.py:182-214,
+                                          csrc/flash_attn/src/mask.h:172-173
+  * ALiBi bias                            tests/test_flash_attn.py:29-55,
+                                          csrc/flash_attn/src/mask.h:148-165
+  * tanh soft-cap                         csrc/flash_attn/flash_api.cpp:130-134
+  * LSE definition (natural log)          csrc/flash_attn/src/softmax.h:169-186
+  * GQA head mapping h -> h // (H/H_k)    csrc/flash_attn/src/flash_fwd_kernel.h:155
+  * fp8 forward (descales, bf16 out)      flash_attn/cute/testing.py:326-470
+  * split-KV combine                      csrc/flash_attn/src/flash_fwd_kernel.h:1117-1299
+  * paged-KV gather                       csrc/flash_attn/src/flash_fwd_kernel.h:592-597
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+NEG_INF = float("-inf")
+
+
+def visible_mask(
+    seqlen_q: int,
+    seqlen_k: int,
+    causal: bool = False,
+    window: Tuple[int, int] = (-1, -1),
+    q_lens: Optional[torch.Tensor] = None,  # (b,) valid query count per batch
+    k_lens: Optional[torch.Tensor] = None,  # (b,) valid key count per batch
+    device=None,
+) -> Optional[torch.Tensor]:
+    """Boolean (b|1, 1, sq, sk) tensor, True where key j is visible to query i.
+
+    Key j is visible to query i iff  lo(i) <= j <= hi(i)  and j < k_len, with
+      shift = k_len - q_len                      (bottom-right alignment)
+      hi(i) = i + shift + window_right           (window_right = 0 when causal)
+      lo(i) = i + shift - window_left            (only if window_left >= 0)
+    """
+    wl, wr = window
+    if causal:
+        wr = 0
+    nb = 1
+    if q_lens is not None:
+        nb = q_lens.numel()
+    if k_lens is not None:
+        nb = k_lens.numel()
+    i = torch.arange(seqlen_q, device=device).view(1, 1, seqlen_q, 1)
+    j = torch.arange(seqlen_k, device=device).view(1, 1, 1, seqlen_k)
+    sk = (
+        torch.full((nb, 1, 1, 1), seqlen_k, device=device, dtype=torch.long)
+        if k_lens is None
+        else k_lens.view(nb, 1, 1, 1).long()
+    )
+    sq = (
+        torch.full((nb, 1, 1, 1), seqlen_q, device=device, dtype=torch.long)
+        if q_lens is None
+        else q_lens.view(nb, 1, 1, 1).long()
+    )
+    vis = j < sk
+    if wl < 0 and wr < 0:
+        return vis if k_lens is not None else None
+    shift = sk - sq
+    if wr >= 0:
+        vis = vis & (j <= i + shift + wr)
+    if wl >= 0:
+        vis = vis & (j >= i + shift - wl)
+    return vis
+
+
+def alibi_bias(
+    slopes: torch.Tensor,  # (h,) or (b,h) fp32
+    seqlen_q: int,
+    seqlen_k: int,
+    q_lens: Optional[torch.Tensor] = None,
+    k_lens: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """bias[b,h,i,j] = -slope[b,h] * |i + (k_len - q_len) - j|.
+
+    (For causal masks the reference adds +slope*j instead, which differs from this
+    by a per-row constant and therefore yields the same softmax; mask.h:148-165.)
+    """
+    if slopes.dim() == 1:
+        slopes = slopes.unsqueeze(0)
+    b = slopes.shape[0]
+    dev = slopes.device
+    i = torch.arange(seqlen_q, device=dev).view(1, 1, seqlen_q, 1)
+    j = torch.arange(seqlen_k, device=dev).view(1, 1, 1, seqlen_k)
+    sk = seqlen_k if k_lens is None else k_lens.view(-1, 1, 1, 1).long()
+    sq = seqlen_q if q_lens is None else q_lens.view(-1, 1, 1, 1).long()
+    rel = (i + sk - sq - j).abs().to(torch.float32)
+    return -slopes.view(b, -1, 1, 1).to(torch.float32) * rel
+
+
+def attention_oracle(
+    q: torch.Tensor,  # (b, sq, h, d)
+    k: torch.Tensor,  # (b, sk, h_k, d)
+    v: torch.Tensor,  # (b, sk, h_k, dv)
+    softmax_scale: Optional[float] = None,
+    causal: bool = False,
+    window: Tuple[int, int] = (-1, -1),
+    softcap: float = 0.0,
+    alibi_slopes: Optional[torch.Tensor] = None,
+    q_lens: Optional[torch.Tensor] = None,
+    k_lens: Optional[torch.Tensor] = None,
+    compute_dtype: torch.dtype = torch.float32,
+    p_dtype: Optional[torch.dtype] = None,  # quantise P like the kernel does (bf16 / e4m3)
+    q_descale: Optional[torch.Tensor] = None,  # (b, h_k) fp8 only
+    k_descale: Optional[torch.Tensor] = None,
+    v_descale: Optional[torch.Tensor] = None,
+    lse_masked_value: float = float("inf"),
+):
+    """Returns (out (b,sq,h,dv) in q's dtype [bf16 if q is fp8], lse (b,h,sq) fp32).
+
+    Rows with no visible key give out = 0 and lse = +inf (FA2 non-split convention,
+    softmax.h:180) unless ``lse_masked_value`` says otherwise (-inf for split partials).
+    """
+    out_dtype = q.dtype
+    if q.dtype in (torch.float8_e4m3fn, torch.float8_e5m2):
+        out_dtype = torch.bfloat16
+    b, sq, h, d = q.shape
+    sk, hk = k.shape[1], k.shape[2]
+    g = h // hk
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(d)
+    qf, kf, vf = q.to(compute_dtype), k.to(compute_dtype), v.to(compute_dtype)
+    if q_descale is not None:
+        qf = qf * q_descale.to(compute_dtype).repeat_interleave(g, dim=1).view(b, 1, h, 1)
+    if k_descale is not None:
+        kf = kf * k_descale.to(compute_dtype).view(b, 1, hk, 1)
+    if v_descale is not None:
+        vf = vf * v_descale.to(compute_dtype).view(b, 1, hk, 1)
+    if g > 1:
+        kf = kf.repeat_interleave(g, dim=2)
+        vf = vf.repeat_interleave(g, dim=2)
+    s = torch.einsum("bihd,bjhd->bhij", qf, kf).float() * softmax_scale
+    if softcap > 0:
+        s = torch.tanh(s / softcap) * softcap
+    if alibi_slopes is not None:
+        s = s + alibi_bias(alibi_slopes, sq, sk, q_lens, k_lens)
+    vis = visible_mask(sq, sk, causal, window, q_lens, k_lens, device=q.device)
+    if vis is not None:
+        s = s.masked_fill(~vis, NEG_INF)
+    m = s.amax(dim=-1, keepdim=True)
+    m_safe = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
+    e = torch.exp(s - m_safe)
+    denom = e.sum(dim=-1, keepdim=True)
+    lse = (m_safe + torch.log(denom)).squeeze(-1)
+    dead = denom.squeeze(-1) == 0
+    lse = torch.where(dead, torch.full_like(lse, lse_masked_value), lse)
+    if p_dtype is not None:
+        # the kernels quantise the un-normalised probabilities, then divide
+        p = e.to(p_dtype).to(compute_dtype)
+        o = torch.einsum("bhij,bjhd->bihd", p, vf) / denom.clamp_min(1e-30).permute(0, 2, 1, 3).to(compute_dtype)
+    else:
+        p = (e / denom.clamp_min(1e-30)).to(compute_dtype)
+        o = torch.einsum("bhij,bjhd->bihd", p, vf)
+    o = o.masked_fill(dead.permute(0, 2, 1).unsqueeze(-1), 0.0)
+    if q_lens is not None:
+        qvalid = torch.arange(sq, device=q.device).view(1, sq) < q_lens.view(-1, 1)
+        o = o.masked_fill(~qvalid.view(b, sq, 1, 1), 0.0)
+    return o.to(out_dtype), lse
+
+
+def attention_oracle_bwd(q, k, v, dout, **kw):
+    """(out, lse, dq, dk, dv) with fp32 autograd through ``attention_oracle``.
+
+    Reference for dQ/dK/dV: flash_bwd_kernel.h:457-724 computes exactly the vjp of the
+    forward; autograd of the fp32 restatement is the oracle (as in
+    tests/test_flash_attn.py:1060-1100)."""
+    qf = q.detach().float().requires_grad_(True)
+    kf = k.detach().float().requires_grad_(True)
+    vf = v.detach().float().requires_grad_(True)
+    out, lse = attention_oracle(qf, kf, vf, **kw)
+    dq, dk, dv = torch.autograd.grad(out, (qf, kf, vf), dout.float())
+    return out.detach(), lse.detach(), dq, dk, dv
+
+
+def combine_oracle(o_partial: torch.Tensor, lse_partial: torch.Tensor, out_dtype=torch.bfloat16):
+    """Split-KV combine.  o_partial (splits, b, h, sq, d) fp32, lse_partial (splits, b, h, sq).
+
+    lse = logsumexp_s(lse_s); out = sum_s exp(lse_s - lse) * o_s.  If every partial is
+    -inf the final lse is +inf and out = 0 (flash_fwd_kernel.h:1196,1204)."""
+    lse_max = lse_partial.amax(dim=0)
+    lse_max_safe = torch.where(torch.isfinite(lse_max), lse_max, torch.zeros_like(lse_max))
+    w = torch.exp(lse_partial - lse_max_safe)
+    tot = w.sum(dim=0)
+    lse = torch.log(tot) + lse_max_safe
+    dead = tot == 0
+    lse = torch.where(dead, torch.full_like(lse, float("inf")), lse)
+    scale = torch.where(dead.unsqueeze(0), torch.zeros_like(w), w / tot.clamp_min(1e-30))
+    out = (scale.unsqueeze(-1) * o_partial).sum(dim=0)
+    return out.to(out_dtype), lse
+
+
+def gather_paged_kv(cache: torch.Tensor, block_table: torch.Tensor, seqlen: int) -> torch.Tensor:
+    """cache (num_blocks, page, h_k, d), block_table (b, max_blocks) -> (b, seqlen, h_k, d).
+
+    logical position p of batch b lives at cache[block_table[b, p // page], p % page]."""
+    page = cache.shape[1]
+    nblk = (seqlen + page - 1) // page
+    g = cache[block_table[:, :nblk].long()]  # (b, nblk, page, h_k, d)
+    b = block_table.shape[0]
+    return g.reshape(b, nblk * page, cache.shape[2], cache.shape[3])[:, :seqlen]
+
+
+def attention_oracle_varlen(q, k, v, cu_q, cu_k, max_q, max_k, **kw):
+    """Packed varlen wrapper: q (total_q,h,d), k/v (total_k,h_k,d) -> out (total_q,h,d), lse (h,total_q)."""
+    nb = cu_q.numel() - 1
+    h, d = q.shape[1], q.shape[2]
+    out = torch.zeros_like(q if q.dtype not in (torch.float8_e4m3fn,) else q.to(torch.bfloat16))
+    lse = torch.zeros(h, q.shape[0], dtype=torch.float32, device=q.device)
+    for i in range(nb):
+        a, b_ = int(cu_q[i]), int(cu_q[i + 1])
+        c, e = int(cu_k[i]), int(cu_k[i + 1])
+        if b_ == a:
+            continue
+        kw_i = dict(kw)
+        if kw_i.get("alibi_slopes") is not None and kw_i["alibi_slopes"].dim() == 2:
+            kw_i["alibi_slopes"] = kw_i["alibi_slopes"][i : i + 1]
+        if e == c:
+            lse[:, a:b_] = float("inf")
+            continue
+        o, l = attention_oracle(q[a:b_].unsqueeze(0), k[c:e].unsqueeze(0), v[c:e].unsqueeze(0), **kw_i)
+        out[a:b_] = o[0]
+        lse[:, a:b_] = l[0]
+    return out, lse
+
+
+def attention_flops(b, h, sq, sk, d, causal=False, window=(-1, -1), mode="fwd"):
+    """Reference FLOP convention (flash_attn/cute/bench_utils.py:15-48,
+    benchmarks/benchmark_flash_attention.py:27-30): fwd = 4*b*h*pairs*d where pairs is
+    the number of visible (i,j) pairs; bwd = 2.5x, fwd_bwd = 3.5x."""
+    wl, wr = window
+    if causal:
+        wr = 0
+    if wl < 0 and wr < 0:
+        pairs = sq * sk
+    else:
+        i = torch.arange(sq, dtype=torch.long)
+        hi = torch.clamp(i + sk - sq + (wr if wr >= 0 else sk), max=sk - 1)
+        lo = torch.clamp(i + sk - sq - wl, min=0) if wl >= 0 else torch.zeros_like(i)
+        pairs = int(torch.clamp(hi - lo + 1, min=0).sum())
+    f = 4 * b * h * pairs * d
+    return {"fwd": f, "bwd": 2.5 * f, "fwd_bwd": 3.5 * f}[mode]
