@@ -1,0 +1,31 @@
+"""flash_attention_b200 — B200-native (sm_100a) fused attention behind the flash_attn operator API.
+
+    from flash_attention_b200 import flash_attn_func, flash_attn_varlen_func, flash_attn_with_kvcache
+
+or, to run the reference's own `flash_attn/flash_attn_interface.py` unchanged on these kernels:
+
+    import flash_attention_b200; flash_attention_b200.install()
+"""
+import sys
+
+__version__ = "0.1.0"
+
+
+def install(name: str = "flash_attn_2_cuda"):
+    """Register this package's operator module as `flash_attn_2_cuda` (the extension module the
+    reference's flash_attn_interface.py imports, flash_attn/flash_attn_interface.py:23)."""
+    from . import flash_attn_2_cuda as mod
+
+    sys.modules[name] = mod
+    return mod
+
+
+def __getattr__(attr):
+    # lazy: importing the package must not require torch/CUDA (build() runs on a CPU box)
+    if attr in ("flash_attn_func", "flash_attn_varlen_func", "flash_attn_with_kvcache", "flash_attn_qkvpacked_func",
+                "flash_attn_kvpacked_func", "flash_attn_varlen_qkvpacked_func", "flash_attn_varlen_kvpacked_func",
+                "flash_attn_combine"):
+        from . import flash_attn_interface as m
+
+        return getattr(m, attr)
+    raise AttributeError(attr)

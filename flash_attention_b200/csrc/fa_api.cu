@@ -1,0 +1,375 @@
+// fa_api.cu — C-ABI host layer of libfa_b200.so: argument checks, mask canonicalisation, split-KV
+// heuristic, TMA tensor-map construction and kernel dispatch.  Restates the host logic of the
+// reference's csrc/flash_attn/flash_api.cpp (set_params_fprop :44-177, set_params_splitkv :317-347,
+// num_splits_heuristic :281-315, mha_fwd :368-536, mha_varlen_fwd :538-788, mha_fwd_kvcache :1243-1532)
+// for the B200 kernels; no torch types cross this boundary (see include/fa_b200.h).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/fa_b200.h"
+#include "fa_api_common.h"
+#include "fa_combine.cuh"
+#include "fa_fwd_sm100.cuh"
+
+namespace fa {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+int set_error(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+
+// ---------------------------------------------------------------- driver entry point for TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// rank-N tiled tensor map, 128-byte swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES
+// for dims 1..rank-1.
+int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i] ? dims[i] : 1;
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  for (int i = 1; i < rank; ++i) {
+    if (gstr[i - 1] % 16 != 0) return set_error("tensor strides must be multiples of 16 bytes (TMA)");
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_error("tensor base pointers must be 16-byte aligned (TMA)");
+  CUresult r = fn(out, dt, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u,%u]", int(r),
+             rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+             (unsigned long long)(rank > 3 ? gdim[3] : 0), (unsigned long long)(rank > 4 ? gdim[4] : 0), bdim[0],
+             bdim[1], bdim[2], rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0);
+    return set_error(buf);
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Fewest splits that reach >= 85 % of the best achievable wave efficiency; 1 if the grid already
+// covers >= 80 % of the SMs (restates flash_api.cpp:281-315 for a 1-CTA-per-SM kernel).
+int splits_heuristic(int ctas, int sms, int n_blocks, int max_splits) {
+  if (ctas >= 0.8f * sms) return 1;
+  max_splits = std::min(std::min(max_splits, sms), n_blocks);
+  if (max_splits <= 1) return 1;
+  float best = 0.f;
+  auto eligible = [&](int s) { return s == 1 || cdiv(n_blocks, s) != cdiv(n_blocks, s - 1); };
+  auto eff_of = [&](int s) {
+    float waves = float(ctas) * s / sms;
+    return waves / std::ceil(waves);
+  };
+  for (int s = 1; s <= max_splits; ++s)
+    if (eligible(s)) best = std::max(best, eff_of(s));
+  for (int s = 1; s <= max_splits; ++s)
+    if (eligible(s) && eff_of(s) >= 0.85f * best) return s;
+  return 1;
+}
+
+enum FwdMode { kDense = 0, kVarlen = 1, kKvcache = 2 };
+
+struct FwdPlan {
+  int kD;        // padded head dim of the kernel (64 or 128)
+  int gp;        // packed heads
+  int num_m_blocks;
+  int num_splits;
+  int has_left, has_right, wl, wr;
+  size_t ws_bytes;
+};
+
+static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
+  if (a.dtype != FA_B200_FP16 && a.dtype != FA_B200_BF16) {
+    if (a.dtype == FA_B200_FP8_E4M3) return set_error("fp8 e4m3 forward is not built in this revision");
+    return set_error("FlashAttention only support fp16 and bf16 data type");
+  }
+  if (!a.q || !a.k || !a.v || !a.out || !a.softmax_lse) return set_error("q, k, v, out, softmax_lse must be non-null");
+  if (a.b <= 0) return set_error("batch size must be positive");
+  if (a.d <= 0 || a.d > 256) return set_error("FlashAttention forward only supports head dimension at most 256");
+  if (a.d % 8 != 0) return set_error("head_size should be a multiple of 8");
+  if (a.d > 128) return set_error("this build of fa_b200 supports head dimension at most 128");
+  if (a.h <= 0 || a.h_k <= 0 || a.h % a.h_k != 0)
+    return set_error("Number of heads in key/value must divide number of heads in query");
+  if (a.softcap < 0.f) return set_error("softcap must be non-negative");
+  if (mode == kVarlen && (!a.cu_seqlens_q || !a.cu_seqlens_k)) return set_error("cu_seqlens_q and cu_seqlens_k are required");
+  if (a.block_table) {
+    if (a.page_block_size <= 0 || a.page_block_size % 128 != 0)
+      return set_error("Paged KV cache block size must be divisible by 128");
+    if (a.num_pages <= 0) return set_error("num_pages must be positive for a paged KV cache");
+  }
+  pl->kD = a.d <= 64 ? 64 : 128;
+  // window canonicalisation (flash_api.cpp:414-419, set_params_fprop :150-164)
+  int wl = a.window_size_left, wr = a.window_size_right;
+  int causal = a.is_causal;
+  if (wl >= a.seqlen_k) wl = -1;
+  if (wr >= a.seqlen_k) wr = -1;
+  if (a.seqlen_q == 1 && !a.alibi_slopes && mode != kVarlen) causal = 0;  // causal=true == causal=false for sq=1
+  if (causal) wr = 0;
+  pl->has_left = wl >= 0;
+  pl->has_right = wr >= 0;
+  pl->wl = wl;
+  pl->wr = wr;
+  // GQA head packing: fold the g query heads of one KV head into the M dimension when a tile of
+  // 256 query positions would otherwise be mostly empty (decode / short queries).
+  const int g = a.h / a.h_k;
+  int gp = 1;
+  if (g > 1 && is_pow2(g) && g <= 128) {
+    const int sq = a.seqlen_q;
+    const double eff_unpacked = double(sq) / (cdiv(sq, 256) * 256);
+    const double eff_packed = double(sq) * g / (cdiv(sq * g, 256) * 256);
+    if (eff_packed > 1.2 * eff_unpacked) gp = g;
+  }
+  pl->gp = gp;
+  pl->num_m_blocks = cdiv(a.seqlen_q * gp, 256);
+  // split-KV (flash_api.cpp:317-347): heuristic when num_splits == 0; never for packed-varlen q
+  int splits = a.num_splits;
+  if (splits < 0) return set_error("num_splits must be non-negative");
+  if (mode == kVarlen) {
+    if (a.block_table && splits > 1) return set_error("num_splits > 1 is not supported for varlen paged KV");
+    splits = 1;
+  } else if (splits == 0) {
+    const int n_blocks = cdiv(a.seqlen_k, 128);
+    splits = splits_heuristic(pl->num_m_blocks * (a.h / gp) * a.b, num_sms(), n_blocks, 128);
+  }
+  if (splits > 128) return set_error("num_splits > 128 not supported");
+  pl->num_splits = splits;
+  pl->ws_bytes = 0;
+  if (splits > 1) {
+    const size_t rows = size_t(splits) * a.b * a.h * a.seqlen_q;
+    pl->ws_bytes = rows * pl->kD * sizeof(float) + rows * sizeof(float);
+    pl->ws_bytes = (pl->ws_bytes + 255) & ~size_t(255);
+  }
+  return 0;
+}
+
+template <typename T, int kD>
+static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+  using Cfg = FwdCfg<kD>;
+  static bool configured = false;
+  auto kern = fa_fwd_kernel<T, kD>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(fwd): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_fwd_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream) {
+  FwdPlan pl;
+  if (int rc = plan_fwd(a, mode, &pl)) return rc;
+  if (pl.num_splits > 1 && (!a.workspace || a.workspace_bytes < pl.ws_bytes))
+    return set_error("workspace too small for split-KV (query fa_b200_fwd_workspace_bytes)");
+  if (a.seqlen_q == 0 || (mode == kVarlen && a.total_q == 0)) return 0;
+
+  const int esz = 2;
+  const CUtensorMapDataType dt = a.dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const int g = a.h / a.h_k, gp = pl.gp;
+  FwdKernelParams kp;
+  memset(&kp, 0, sizeof kp);
+  {
+    // Q: (d, gp, rows, h/gp, b)
+    const bool varlen = a.cu_seqlens_q != nullptr;
+    uint64_t dims[5] = {uint64_t(a.d), uint64_t(gp), uint64_t(varlen ? a.total_q : a.seqlen_q), uint64_t(a.h / gp),
+                        uint64_t(varlen ? 1 : a.b)};
+    uint64_t str[4] = {uint64_t(a.q_head_stride) * esz, uint64_t(a.q_row_stride) * esz,
+                       uint64_t(a.q_head_stride) * gp * esz,
+                       uint64_t(varlen ? int64_t(a.total_q) * a.q_row_stride : a.q_batch_stride) * esz};
+    if (dims[4] == 1) str[3] = dims[2] * str[1];  // any valid value
+    uint32_t box[5] = {64, uint32_t(gp), uint32_t(128 / gp), 1, 1};
+    if (int rc = make_tmap(&kp.tm_q, dt, 5, a.q, dims, str, box)) return rc;
+  }
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? a.k : a.v;
+    const int64_t bs = which == 0 ? a.k_batch_stride : a.v_batch_stride;
+    const int64_t rs = which == 0 ? a.k_row_stride : a.v_row_stride;
+    const int64_t hs = which == 0 ? a.k_head_stride : a.v_head_stride;
+    uint64_t rows, nb;
+    if (a.block_table) { rows = a.page_block_size; nb = a.num_pages; }
+    else if (a.cu_seqlens_k) { rows = a.total_k; nb = 1; }
+    else { rows = a.seqlen_k; nb = a.b; }
+    uint64_t dims[4] = {uint64_t(a.d), rows, uint64_t(a.h_k), nb};
+    uint64_t str[3] = {uint64_t(rs) * esz, uint64_t(hs) * esz, uint64_t(bs) * esz};
+    if (nb == 1) str[2] = rows * str[0];
+    uint32_t box[4] = {64, 128, 1, 1};
+    if (int rc = make_tmap(which == 0 ? &kp.tm_k : &kp.tm_v, dt, 4, base, dims, str, box)) return rc;
+  }
+  kp.o = a.out;
+  kp.lse = a.softmax_lse;
+  kp.o_batch_stride = a.o_batch_stride;
+  kp.o_row_stride = a.o_row_stride;
+  kp.o_head_stride = a.o_head_stride;
+  kp.cu_seqlens_q = a.cu_seqlens_q;
+  kp.cu_seqlens_k = a.cu_seqlens_k;
+  kp.seqused_k = a.seqused_k;
+  kp.block_table = a.block_table;
+  kp.block_table_batch_stride = a.block_table_batch_stride;
+  kp.alibi_slopes = a.alibi_slopes;
+  kp.alibi_batch_stride = a.alibi_slopes_batch_stride;
+  kp.debug_s = a.debug_s;
+  kp.b = a.b; kp.h = a.h; kp.h_k = a.h_k; kp.sq = a.seqlen_q; kp.sk = a.seqlen_k; kp.d = a.d;
+  kp.g = g; kp.gp = gp; kp.total_q = a.total_q;
+  kp.page_size = a.block_table ? a.page_block_size : 0;
+  kp.num_splits = pl.num_splits;
+  kp.has_left = pl.has_left; kp.has_right = pl.has_right; kp.wl = pl.wl; kp.wr = pl.wr;
+  kp.reverse_m = pl.has_right ? 1 : 0;
+  if (a.softcap > 0.f) {  // s' = tanh(s * scale / softcap) * softcap  (flash_api.cpp:130-134)
+    kp.softcap_pre = a.softmax_scale / a.softcap;
+    kp.scale = a.softcap;
+  } else {
+    kp.softcap_pre = 0.f;
+    kp.scale = a.softmax_scale;
+  }
+  kp.scale_log2 = kp.scale * float(M_LOG2E);
+  if (pl.num_splits > 1) {
+    const size_t rows = size_t(pl.num_splits) * a.b * a.h * a.seqlen_q;
+    kp.o_accum = reinterpret_cast<float*>(a.workspace);
+    kp.lse_accum = kp.o_accum + rows * pl.kD;
+  }
+  dim3 grid(pl.num_m_blocks, a.h / gp, a.b * pl.num_splits);
+  int rc;
+  if (a.dtype == FA_B200_BF16) {
+    rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream)
+                     : launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream);
+  } else {
+    rc = pl.kD == 64 ? launch_fwd_kernel<__half, 64>(kp, grid, stream) : launch_fwd_kernel<__half, 128>(kp, grid, stream);
+  }
+  if (rc) return rc;
+  if (pl.num_splits > 1) {
+    CombineParams cp;
+    cp.o_partial = kp.o_accum;
+    cp.lse_partial = kp.lse_accum;
+    cp.out = a.out;
+    cp.lse = a.softmax_lse;
+    cp.rows = int64_t(a.b) * a.h * a.seqlen_q;
+    cp.splits = pl.num_splits;
+    cp.d = a.d;
+    cp.d_part = pl.kD;
+    cp.h = a.h;
+    cp.sq = a.seqlen_q;
+    cp.obs = a.o_batch_stride; cp.ors = a.o_row_stride; cp.ohs = a.o_head_stride;
+    const unsigned blocks = unsigned((cp.rows + 7) / 8);
+    if (a.dtype == FA_B200_BF16) fa_combine_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(cp);
+    else fa_combine_kernel<__half><<<blocks, 256, 0, stream>>>(cp);
+    g_launch_count++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(std::string("fa_combine_kernel launch: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+int fa_b200_mha_fwd(const fa_b200_fwd_args* args, fa_b200_stream_t stream) {
+  if (!args) return set_error("null args");
+  if (args->cu_seqlens_q || args->cu_seqlens_k || args->block_table)
+    return set_error("fa_b200_mha_fwd takes dense tensors; use the varlen / kvcache entry points");
+  return run_fwd(*args, kDense, static_cast<cudaStream_t>(stream));
+}
+
+int fa_b200_mha_varlen_fwd(const fa_b200_fwd_args* args, fa_b200_stream_t stream) {
+  if (!args) return set_error("null args");
+  return run_fwd(*args, kVarlen, static_cast<cudaStream_t>(stream));
+}
+
+int fa_b200_mha_fwd_kvcache(const fa_b200_fwd_args* args, fa_b200_stream_t stream) {
+  if (!args) return set_error("null args");
+  if (args->cu_seqlens_q || args->cu_seqlens_k) return set_error("kvcache forward takes batched (non-packed) q");
+  return run_fwd(*args, kKvcache, static_cast<cudaStream_t>(stream));
+}
+
+static FwdMode mode_of(const fa_b200_fwd_args* a) { return a->cu_seqlens_q ? kVarlen : (a->block_table || a->seqused_k ? kKvcache : kDense); }
+
+size_t fa_b200_fwd_workspace_bytes(const fa_b200_fwd_args* args) {
+  FwdPlan pl;
+  if (!args || plan_fwd(*args, mode_of(args), &pl)) return 0;
+  return pl.ws_bytes;
+}
+
+int fa_b200_fwd_num_splits(const fa_b200_fwd_args* args) {
+  FwdPlan pl;
+  if (!args || plan_fwd(*args, mode_of(args), &pl)) return -1;
+  return pl.num_splits;
+}
+
+int fa_b200_fwd_combine(const float* o_partial, const float* lse_partial, void* out, float* lse, int32_t num_splits,
+                        int64_t rows, int32_t d, int32_t dtype, fa_b200_stream_t stream) {
+  if (!o_partial || !lse_partial || !out) return set_error("null pointer");
+  if (d % 4 != 0) return set_error("combine: d must be a multiple of 4");
+  if (num_splits < 1) return set_error("combine: num_splits must be >= 1");
+  if (rows <= 0) return 0;
+  CombineParams cp;
+  cp.o_partial = o_partial; cp.lse_partial = lse_partial; cp.out = out; cp.lse = lse;
+  cp.rows = rows; cp.splits = num_splits; cp.d = d; cp.d_part = d; cp.h = 1; cp.sq = 1;
+  cp.obs = d; cp.ors = 0; cp.ohs = 0;
+  const unsigned blocks = unsigned((rows + 7) / 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == FA_B200_BF16) fa_combine_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(cp);
+  else if (dtype == FA_B200_FP16) fa_combine_kernel<__half><<<blocks, 256, 0, s>>>(cp);
+  else return set_error("combine: output dtype must be fp16 or bf16");
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_combine_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int fa_b200_num_splits_heuristic(int batch_nheads_mblocks, int num_sms_, int num_n_blocks, int max_splits) {
+  return splits_heuristic(batch_nheads_mblocks, num_sms_, num_n_blocks, max_splits);
+}
+
+const char* fa_b200_last_error(void) { return g_last_error.c_str(); }
+size_t fa_b200_sizeof_fwd_args(void) { return sizeof(fa_b200_fwd_args); }
+size_t fa_b200_sizeof_bwd_args(void) { return sizeof(fa_b200_bwd_args); }
+const char* fa_b200_version(void) { return "fa_b200 0.1 (sm_100a)"; }
+uint64_t fa_b200_launch_count(void) { return g_launch_count.load(); }
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// fa_fwd_sm100.cuh — forward attention mainloop for sm_100a (B200).
+//
+// One CTA owns up to two 128-row query tiles ("tile 0/1", 256 packed rows) of one (batch, head-slot,
+// split) and streams the K/V blocks of that work item right-to-left (masked blocks first, like the
+// reference: csrc/flash_attn/src/flash_fwd_kernel.h:138-140,274).
+//
+//   warp 0-3  softmax warpgroup for tile 0 : tcgen05.ld S row -> mask -> online max/sum -> exp2 ->
+//   warp 4-7  softmax warpgroup for tile 1   tcgen05.st P (aliases S in TMEM) ; lazy O rescale ; epilogue
+//   warp 8    MMA issuer (one elected thread): S_i = Q_i K^T (SS), O_i += P_i V (TS, P read from TMEM)
+//   warp 9    TMA producer: Q tiles once, K/V blocks through a 5-deep shared-memory ring
+//
+// TMEM (512 columns): S0 @0, S1 @128, O0 @256, O1 @384 (fp32); P_i overwrites S_i in place as packed
+// 16-bit pairs.  S/P never touch HBM.  The two tiles ping-pong on the tensor pipe: while warpgroup i
+// runs softmax on S_i the MMA thread executes the other tile's GEMMs.
+//
+// Semantics follow the reference kernels (file:line cited inline): bottom-right aligned causal /
+// sliding-window masks (mask.h:172-173), ALiBi (mask.h:148-165, flash_fwd_kernel.h:294), tanh
+// soft-cap (flash_api.cpp:130-134), LSE (softmax.h:169-186), GQA (flash_fwd_kernel.h:155), split-KV
+// partials (flash_fwd_kernel.h:535-582,1026-1038), paged KV (flash_fwd_kernel.h:592-597).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "fa_ptx.cuh"
+
+namespace fa {
+
+struct FwdKernelParams {
+  CUtensorMap tm_q;  // 5-D: (d, gp, rows, h/gp, b)      box (64, gp, 128/gp, 1, 1)
+  CUtensorMap tm_k;  // 4-D: (d, rows, h_k, b|pages|1)   box (64, 128, 1, 1)
+  CUtensorMap tm_v;
+  void* o;
+  float* lse;
+  float* o_accum;    // (splits, b, h, sq, kD) fp32 when num_splits > 1
+  float* lse_accum;  // (splits, b, h, sq)
+  int64_t o_batch_stride, o_row_stride, o_head_stride;
+  const int* cu_seqlens_q;
+  const int* cu_seqlens_k;
+  const int* seqused_k;
+  const int* block_table;
+  int64_t block_table_batch_stride;
+  const float* alibi_slopes;
+  int64_t alibi_batch_stride;
+  const float* q_descale;
+  const float* k_descale;
+  const float* v_descale;
+  int64_t q_descale_bs, k_descale_bs, v_descale_bs;
+  float* debug_s;
+  int b, h, h_k, sq, sk, d;
+  int g;         // h / h_k
+  int gp;        // query heads packed into the M dimension (1 or g)
+  int total_q;   // varlen: rows of the packed q tensor (LSE row stride), else 0
+  int page_size; // 0 = not paged
+  int num_splits;
+  int has_right, has_left;  // window limits active (causal => has_right, wr = 0)
+  int wl, wr;
+  int reverse_m;            // schedule heavy m-blocks first (causal)
+  float scale;              // effective softmax scale (softcap if softcap > 0)
+  float scale_log2;         // scale * log2(e)
+  float softcap_pre;        // softmax_scale / softcap, 0 = off
+};
+
+template <int kD>
+struct FwdCfg {
+  static constexpr int kBlockM = 128;
+  static constexpr int kBlockN = 128;
+  static constexpr int kStages = 5;
+  static constexpr int kThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle}
+  static constexpr int kPanels = kD / 64;                 // 64-element (128 B) swizzle panels per row
+  static constexpr int kPanelBytes = 128 * 128;           // 128 rows x 128 B
+  static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
+  static constexpr int kSmemQ = 2 * kTileBytes;
+  static constexpr int kSmemKV = kStages * kTileBytes;
+  static constexpr int kNumBars = 2 + 2 * kStages + 6;
+  static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
+};
+
+// 16-bit element traits
+template <typename T> struct Elt;
+template <> struct Elt<__nv_bfloat16> {
+  static constexpr uint32_t kFmt = 1;
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return pack_bf16(lo, hi); }
+};
+template <> struct Elt<__half> {
+  static constexpr uint32_t kFmt = 0;
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return pack_f16(lo, hi); }
+};
+
+__device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+template <typename T, int kD>
+__global__ void __launch_bounds__(FwdCfg<kD>::kThreads, 1)
+fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
+  using Cfg = FwdCfg<kD>;
+  constexpr int S = Cfg::kStages;
+  constexpr float kNegInf = -INFINITY;
+
+  // ------------------------------------------------------------------ work item
+  const int num_m_blocks = gridDim.x;
+  const int m_block = p.reverse_m ? (num_m_blocks - 1 - blockIdx.x) : blockIdx.x;
+  const int slot = blockIdx.y;                  // index over h / gp
+  const int bidb = blockIdx.z / p.num_splits;
+  const int split = blockIdx.z - bidb * p.num_splits;
+
+  int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
+  if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
+  if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
+  if (p.seqused_k) sk_b = p.seqused_k[bidb];
+  const int rows_total = sq_b * p.gp;
+  const int row0 = m_block * 256;
+  if (row0 >= rows_total) return;  // uniform for the whole CTA, nothing allocated yet
+  const int ntiles = (row0 + 128 < rows_total) ? 2 : 1;
+
+  const int hk_idx = (slot * p.gp) / p.g;
+  const int shift = sk_b - sq_b;  // bottom-right alignment (mask.h:172-173)
+  const int nblk_total = ceil_div(sk_b, 128);
+  int n_min = 0, n_max = nblk_total;
+  {
+    const int qpos_lo = row0 / p.gp;
+    int last_row = row0 + 255 < rows_total - 1 ? row0 + 255 : rows_total - 1;
+    const int qpos_hi = last_row / p.gp;
+    if (p.has_right) {
+      int lim = qpos_hi + 1 + shift + p.wr;  // exclusive column limit of the last row
+      int nb = lim <= 0 ? 0 : ceil_div(lim, 128);
+      n_max = nb < n_max ? nb : n_max;
+    }
+    if (p.has_left) {
+      int lo = qpos_lo + shift - p.wl;
+      int nb = lo <= 0 ? 0 : lo / 128;
+      n_min = nb;
+    }
+    if (p.num_splits > 1) {  // equal block ranges per split (flash_fwd_kernel.h:535-543)
+      const int per = ceil_div(nblk_total, p.num_splits);
+      int lo = split * per, hi = (split + 1) * per;
+      n_min = n_min > lo ? n_min : lo;
+      n_max = n_max < hi ? n_max : hi;
+    }
+  }
+  const int nblocks = n_max > n_min ? n_max - n_min : 0;
+
+  // ------------------------------------------------------------------ shared memory carve-up
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = sQ + Cfg::kSmemQ;
+  const uint32_t sBar = sKV + Cfg::kSmemKV;
+  auto bar_q_full = [&](int i) { return sBar + 8u * i; };
+  auto bar_kv_full = [&](int s) { return sBar + 8u * (2 + s); };
+  auto bar_kv_empty = [&](int s) { return sBar + 8u * (2 + S + s); };
+  auto bar_s_full = [&](int i) { return sBar + 8u * (2 + 2 * S + i); };
+  auto bar_p_full = [&](int i) { return sBar + 8u * (4 + 2 * S + i); };
+  auto bar_o_full = [&](int i) { return sBar + 8u * (6 + 2 * S + i); };
+  const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSmemQ + Cfg::kSmemKV + 8 * Cfg::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q);
+    tma_prefetch_desc(&p.tm_k);
+    tma_prefetch_desc(&p.tm_v);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_q_full(i), 1);
+        mbar_init(bar_s_full(i), 1);
+        mbar_init(bar_p_full(i), 4);  // one arrive per softmax warp
+        mbar_init(bar_o_full(i), 1);
+      }
+      for (int s = 0; s < S; ++s) {
+        mbar_init(bar_kv_full(s), 1);
+        mbar_init(bar_kv_empty(s), 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(sTmemPtr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // register re-distribution (per warpgroup): softmax rows live in registers, the MMA/TMA warps need few
+  if (warp >= 8) {
+  reg_dealloc<56>();
+  // ================================================================== TMA producer
+  if (warp == 9) {
+    if (lane == 0 && nblocks > 0) {
+      const int bq = p.cu_seqlens_q ? 0 : bidb;
+      for (int i = 0; i < ntiles; ++i) {
+        mbar_arrive_expect_tx(bar_q_full(i), Cfg::kTileBytes);
+        const int qpos0 = q_off + (row0 + i * 128) / p.gp;
+#pragma unroll
+        for (int pn = 0; pn < Cfg::kPanels; ++pn)
+          tma_load_5d(sQ + i * Cfg::kTileBytes + pn * Cfg::kPanelBytes, &p.tm_q, bar_q_full(i), pn * 64, 0, qpos0,
+                      slot, bq);
+      }
+      int ring = 0;  // running slot counter: K_it -> 2*it, V_it -> 2*it + 1
+      for (int it = 0; it < nblocks; ++it) {
+        const int j = n_max - 1 - it;
+        int row = k_off + j * 128, c3 = p.cu_seqlens_k ? 0 : bidb;
+        if (p.page_size) {
+          const int pos = j * 128;
+          c3 = p.block_table[bidb * p.block_table_batch_stride + pos / p.page_size];
+          row = pos % p.page_size;
+        }
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv, ++ring) {
+          const int s = ring % S;
+          const uint32_t ph = (ring / S) & 1;
+          mbar_wait(bar_kv_empty(s), ph ^ 1, 100 + s);
+          mbar_arrive_expect_tx(bar_kv_full(s), Cfg::kTileBytes);
+          const CUtensorMap* tm = kv == 0 ? &p.tm_k : &p.tm_v;
+#pragma unroll
+          for (int pn = 0; pn < Cfg::kPanels; ++pn)
+            tma_load_4d(sKV + s * Cfg::kTileBytes + pn * Cfg::kPanelBytes, tm, bar_kv_full(s), pn * 64, row, hk_idx,
+                        c3);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ================================================================== MMA issuer
+  else if (warp == 8) {
+    if (nblocks > 0) {
+      constexpr uint32_t fmt = Elt<T>::kFmt;
+      constexpr uint32_t idesc_qk = make_idesc(fmt, fmt, 0, 0, 128, 128);
+      constexpr uint32_t idesc_pv = make_idesc(fmt, fmt, 0, 1, 128, kD);
+      constexpr uint64_t desc_k_major = smem_desc_sw128(16, 1024);
+      constexpr uint64_t desc_mn_major = smem_desc_sw128(Cfg::kPanelBytes, 1024);
+      const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+
+      auto issue_qk = [&](int i, int slot_k) {
+        const uint32_t a0 = sQ + i * Cfg::kTileBytes;
+        const uint32_t b0 = sKV + slot_k * Cfg::kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk) {
+          const uint32_t off = (kk / 4) * Cfg::kPanelBytes + (kk % 4) * 32;
+          mma_ss<false>(tS[i], smem_desc_at(desc_k_major, a0 + off), smem_desc_at(desc_k_major, b0 + off), idesc_qk,
+                        kk > 0);
+        }
+      };
+      auto issue_pv = [&](int i, int slot_v, bool acc) {
+        const uint32_t b0 = sKV + slot_v * Cfg::kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < 128 / 16; ++kk) {
+          mma_ts<false>(tO[i], tS[i] + kk * 8, smem_desc_at(desc_mn_major, b0 + kk * 2048), idesc_pv,
+                        (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+
+      for (int i = 0; i < ntiles; ++i) mbar_wait(bar_q_full(i), 0, 200 + i);
+      // prologue: S_i = Q_i K_0^T
+      mbar_wait(bar_kv_full(0), 0, 210);
+      tc_fence_after();
+      if (lane == 0) {
+        for (int i = 0; i < ntiles; ++i) {
+          issue_qk(i, 0);
+          mma_commit(bar_s_full(i));
+        }
+        mma_commit(bar_kv_empty(0));
+      }
+      __syncwarp();
+      for (int it = 0; it < nblocks; ++it) {
+        const int ring_v = 2 * it + 1, ring_k = 2 * it + 2;
+        const int sv = ring_v % S, sk_ = ring_k % S;
+        const uint32_t phv = (ring_v / S) & 1, phk = (ring_k / S) & 1;
+        const bool more = it + 1 < nblocks;
+        mbar_wait(bar_kv_full(sv), phv, 220);
+        if (it == 0 && n_max == nblk_total && (sk_b & 127)) {
+          // Rows of the last V block beyond seqlen_k may hold garbage (kv-cache tail, next sequence):
+          // P is exactly 0 there but 0 * NaN would poison O, so clear them
+          // (reference: Clear_OOB_MN on the V load, flash_fwd_kernel.h:254-262).
+          const int valid = sk_b - (nblk_total - 1) * 128;
+          const int nvec = (128 - valid) * 8;
+          for (int pn = 0; pn < Cfg::kPanels; ++pn) {
+            uint4* base = reinterpret_cast<uint4*>(smem_gen + Cfg::kSmemQ + sv * Cfg::kTileBytes +
+                                                   pn * Cfg::kPanelBytes + valid * 128);
+            for (int x = lane; x < nvec; x += 32) base[x] = make_uint4(0, 0, 0, 0);
+          }
+          fence_proxy_async();
+          __syncwarp();
+        }
+        for (int i = 0; i < ntiles; ++i) {
+          mbar_wait(bar_p_full(i), it & 1, 230 + i);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_pv(i, sv, it > 0);
+            mma_commit(bar_o_full(i));
+            if (i == ntiles - 1) mma_commit(bar_kv_empty(sv));
+          }
+          if (more) {
+            if (i == 0) {
+              mbar_wait(bar_kv_full(sk_), phk, 240);
+              tc_fence_after();
+            }
+            if (lane == 0) {
+              issue_qk(i, sk_);
+              mma_commit(bar_s_full(i));
+              if (i == ntiles - 1) mma_commit(bar_kv_empty(sk_));
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+  }
+  } else {
+  // ================================================================== softmax warpgroups
+    reg_alloc<224>();
+    const int tile = warp >> 2;
+    if (tile < ntiles) {
+      const int wq = warp & 3;
+      const uint32_t lane_sel = uint32_t(wq * 32) << 16;
+      const uint32_t tS = tmem_base + lane_sel + tile * 128;
+      const uint32_t tO = tmem_base + lane_sel + 256 + tile * 128;
+      const int r = row0 + tile * 128 + wq * 32 + lane;  // packed row of this thread
+      const int qpos = r / p.gp;
+      const int head = slot * p.gp + (r - qpos * p.gp);
+      const bool row_valid = r < rows_total;
+      const float scale_log2 = p.scale_log2;
+      // tile-level limits for the "does this block need masking" test
+      const int t_row_lo = row0 + tile * 128;
+      int t_row_hi = t_row_lo + 127 < rows_total - 1 ? t_row_lo + 127 : rows_total - 1;
+      const int t_qlo = t_row_lo / p.gp, t_qhi = t_row_hi / p.gp;
+      // this row's visible column range [col_lo, col_hi)
+      int col_hi = sk_b, col_lo = 0;
+      if (p.has_right) { int l = qpos + 1 + shift + p.wr; col_hi = l < col_hi ? l : col_hi; }
+      if (p.has_left) { int l = qpos + shift - p.wl; col_lo = l > 0 ? l : 0; }
+      float slope = 0.f;
+      if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + head] / p.scale;
+
+      float m_ref = kNegInf, row_sum = 0.f;
+      for (int it = 0; it < nblocks; ++it) {
+        const int j = n_max - 1 - it;
+        const int col0 = j * 128;
+        mbar_wait(bar_s_full(tile), it & 1, 300 + tile);
+        tc_fence_after();
+        uint32_t su[128];
+        tmem_ld_x32(tS + 0, su);
+        tmem_ld_x32(tS + 32, su + 32);
+        tmem_ld_x32(tS + 64, su + 64);
+        tmem_ld_x32(tS + 96, su + 96);
+        tmem_wait_ld();
+        float* s = reinterpret_cast<float*>(su);
+        if (p.debug_s && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile == 0 && it == 0) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) p.debug_s[(wq * 32 + lane) * 128 + c] = s[c];
+        }
+        if (p.softcap_pre != 0.f) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) s[c] = tanh_approx(s[c] * p.softcap_pre);
+        }
+        if (p.alibi_slopes) {  // bias = -slope * |i + sk - sq - j|  (mask.h:148-165)
+          const float rel0 = float(qpos + shift - col0);
+#pragma unroll
+          for (int c = 0; c < 128; ++c) s[c] = fmaf(-slope, fabsf(rel0 - float(c)), s[c]);
+        }
+        // masking: only blocks that cross a limit of some row of this tile (warp-uniform test)
+        bool need_mask = col0 + 128 > sk_b;
+        if (p.has_right) need_mask |= col0 + 128 > t_qlo + 1 + shift + p.wr;
+        if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
+        if (need_mask) {
+          const int hi = col_hi - col0, lo = col_lo - col0;
+#pragma unroll
+          for (int c = 0; c < 128; ++c) s[c] = (c >= hi || c < lo) ? kNegInf : s[c];
+        }
+        // ---- online softmax: row max with a lazily updated reference (exact after normalisation)
+        float mx = fmax3(s[0], s[1], s[2]);
+#pragma unroll
+        for (int c = 3; c + 1 < 128; c += 2) mx = fmax3(mx, s[c], s[c + 1]);
+        mx = fmaxf(mx, s[127]);
+        const float m_new = fmaxf(m_ref, mx);
+        if (it == 0) {
+          m_ref = m_new;
+        } else {
+          bool need = (m_new - m_ref) * scale_log2 > 8.0f;  // NaN (-inf - -inf) compares false
+          if (m_ref == kNegInf) {  // nothing accumulated yet for this row: O row is 0, sum is 0
+            m_ref = m_new;
+            need = false;
+          }
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(bar_o_full(tile), (it - 1) & 1, 310 + tile);  // PV of the previous block has landed
+            tc_fence_after();
+            const float f = need ? ex2((m_ref - m_new) * scale_log2) : 1.0f;
+#pragma unroll
+            for (int cc = 0; cc < kD; cc += 32) {
+              uint32_t o[32];
+              tmem_ld_x32(tO + cc, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+              tmem_st_x32(tO + cc, o);
+            }
+            row_sum *= f;
+            if (need) m_ref = m_new;
+          }
+        }
+        const float neg_ms = (m_ref == kNegInf) ? 0.f : -m_ref * scale_log2;
+        // ---- P = exp2(S*scale_log2 - m*scale_log2), written back over S as packed 16-bit
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float e0 = ex2(fmaf(s[cc + c], scale_log2, neg_ms));
+            const float e1 = ex2(fmaf(s[cc + c + 1], scale_log2, neg_ms));
+            acc0 += e0;
+            acc1 += e1;
+            pk[c / 2] = Elt<T>::pack(e0, e1);
+          }
+          tmem_st_x16(tS + cc / 2, pk);
+        }
+        row_sum += acc0 + acc1;
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_full(tile));
+      }
+
+      // ---------------------------------------------------------------- epilogue
+      float inv = 0.f, lse_val;
+      const bool dead = !(row_sum > 0.f);  // also catches NaN
+      if (!dead) {
+        inv = 1.0f / row_sum;
+        lse_val = m_ref * p.scale + __logf(row_sum);
+      } else {
+        // fully masked row: +inf for a final result, -inf for a split partial
+        // (softmax.h:180, flash_fwd_kernel.h:544-582)
+        lse_val = p.num_splits > 1 ? kNegInf : INFINITY;
+      }
+      if (nblocks > 0) {
+        mbar_wait(bar_o_full(tile), (nblocks - 1) & 1, 320 + tile);
+        tc_fence_after();
+      }
+      if (p.num_splits > 1) {
+        const int64_t prow = ((int64_t(split) * p.b + bidb) * p.h + head) * p.sq + qpos;
+        float* dst = p.o_accum + prow * kD;
+#pragma unroll
+        for (int cc = 0; cc < kD; cc += 32) {
+          uint32_t o[32];
+          if (nblocks > 0) {
+            tmem_ld_x32(tO + cc, o);
+            tmem_wait_ld();
+          }
+          if (row_valid) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              float4 v4;
+              v4.x = nblocks > 0 ? __uint_as_float(o[c]) * inv : 0.f;
+              v4.y = nblocks > 0 ? __uint_as_float(o[c + 1]) * inv : 0.f;
+              v4.z = nblocks > 0 ? __uint_as_float(o[c + 2]) * inv : 0.f;
+              v4.w = nblocks > 0 ? __uint_as_float(o[c + 3]) * inv : 0.f;
+              *reinterpret_cast<float4*>(dst + cc + c) = v4;
+            }
+          }
+        }
+        if (row_valid) p.lse_accum[prow] = lse_val;
+      } else {
+        T* dst = reinterpret_cast<T*>(p.o) + (p.cu_seqlens_q ? 0 : bidb * p.o_batch_stride) +
+                 int64_t(q_off + qpos) * p.o_row_stride + int64_t(head) * p.o_head_stride;
+#pragma unroll
+        for (int cc = 0; cc < kD; cc += 32) {
+          uint32_t o[32];
+          if (nblocks > 0) {
+            tmem_ld_x32(tO + cc, o);
+            tmem_wait_ld();
+          }
+          if (row_valid) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              if (cc + c < p.d) {  // d is a multiple of 8
+                uint4 v4;
+                if (nblocks > 0) {
+                  v4.x = Elt<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+                  v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+                  v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+                  v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+                } else {
+                  v4 = make_uint4(0, 0, 0, 0);
+                }
+                *reinterpret_cast<uint4*>(dst + cc + c) = v4;
+              }
+            }
+          }
+        }
+        if (row_valid) {
+          if (p.cu_seqlens_q) p.lse[int64_t(head) * p.total_q + q_off + qpos] = lse_val;
+          else p.lse[(int64_t(bidb) * p.h + head) * p.sq + qpos] = lse_val;
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fa

@@ -1,0 +1,146 @@
+/*
+ * fa_b200.h — C ABI of the B200-native fused attention library (libfa_b200.so).
+ *
+ * Drop-in boundary for the reference's `flash_attn_2_cuda` operator module
+ * (csrc/flash_attn/flash_api.cpp:1535-1542).  Every entry point takes plain
+ * device pointers, element strides and sizes — no torch / ATen types — plus the
+ * CUDA stream to launch on.  The reference-side binding (pybind / ctypes stub) is
+ * shown in INTEGRATION.md; the in-repo mirror is
+ * flash_attention_b200/flash_attn_2_cuda.py.
+ *
+ *   reference host entry (flash_api.cpp)            this ABI
+ *   ------------------------------------            ---------------------------
+ *   mha_fwd            :368-536                     fa_b200_mha_fwd
+ *   mha_varlen_fwd     :538-788                     fa_b200_mha_varlen_fwd
+ *   mha_bwd            :800-1008                    fa_b200_mha_bwd
+ *   mha_varlen_bwd     :1010-1241                   fa_b200_mha_varlen_bwd
+ *   mha_fwd_kvcache    :1243-1532                   fa_b200_mha_fwd_kvcache
+ *   num_splits_heuristic :281-315                   fa_b200_num_splits_heuristic
+ *   combine_attn_seqk_parallel (flash_fwd_kernel.h:1117) fa_b200_fwd_combine
+ *   Flash_fwd_params / Flash_bwd_params (flash.h:20-189) fa_b200_fwd_args / fa_b200_bwd_args
+ *
+ * Conventions
+ *   - all strides are in ELEMENTS of the tensor's dtype (like flash.h `index_t`), last-dim stride is 1
+ *   - return value: 0 = ok, non-zero = error; the message is available from
+ *     fa_b200_last_error() (thread-local).  Messages mirror the reference's TORCH_CHECK texts.
+ *   - every call is asynchronous on `stream`; no host sync is performed.
+ *   - scratch memory is caller-owned: query the size with the *_workspace_bytes
+ *     function, allocate (any 256-byte aligned device buffer), pass it in `workspace`.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fa_b200_stream_t; /* cudaStream_t */
+
+enum fa_b200_dtype {
+  FA_B200_FP16 = 0,
+  FA_B200_BF16 = 1,
+  FA_B200_FP8_E4M3 = 2 /* forward only; output is bf16 (spec: hopper/flash_api.cpp mha_fwd, flash_attn/cute/interface.py:637-643) */
+};
+
+/* Forward arguments (dense, varlen, paged-KV decode share one struct; unused pointers are NULL). */
+typedef struct fa_b200_fwd_args {
+  /* tensors */
+  const void* q;   /* dense (b, sq, h, d) | varlen (total_q, h, d) */
+  const void* k;   /* dense (b, sk, h_k, d) | varlen (total_k, h_k, d) | paged (num_blocks, page, h_k, d) */
+  const void* v;
+  void* out;       /* same layout as q; dtype = q's dtype (bf16 for fp8 inputs) */
+  float* softmax_lse; /* dense (b, h, sq) | varlen (h, total_q), fp32 */
+  int64_t q_batch_stride, q_row_stride, q_head_stride;
+  int64_t k_batch_stride, k_row_stride, k_head_stride; /* paged: batch stride = stride between pages */
+  int64_t v_batch_stride, v_row_stride, v_head_stride;
+  int64_t o_batch_stride, o_row_stride, o_head_stride;
+  /* sizes */
+  int32_t b, seqlen_q, seqlen_k, h, h_k, d;  /* varlen: seqlen_* are the max_seqlen_* arguments */
+  int32_t total_q, total_k;                  /* varlen only (rows of the packed tensors), else 0 */
+  int32_t dtype;                             /* enum fa_b200_dtype */
+  /* varlen / kvcache metadata (device pointers, int32) */
+  const int32_t* cu_seqlens_q; /* (b+1) or NULL */
+  const int32_t* cu_seqlens_k; /* (b+1) or NULL */
+  const int32_t* seqused_k;    /* (b) or NULL: number of valid keys per batch (cache_seqlens) */
+  const int32_t* block_table;  /* (b, max_blocks_per_seq) or NULL */
+  int64_t block_table_batch_stride;
+  int32_t page_block_size;     /* multiple of 128 (reference requires 256: flash_api.cpp:1305) */
+  int32_t num_pages;
+  /* masks / score mods */
+  const float* alibi_slopes;   /* (h) or (b,h) fp32, or NULL */
+  int64_t alibi_slopes_batch_stride; /* 0 for (h) */
+  float softmax_scale;
+  float softcap;               /* 0 = off */
+  int32_t is_causal;
+  int32_t window_size_left, window_size_right; /* -1 = infinite */
+  /* fp8 de-scales, (b, h_k) fp32 each or NULL (= 1.0) */
+  const float* q_descale; const float* k_descale; const float* v_descale;
+  int64_t q_descale_batch_stride, k_descale_batch_stride, v_descale_batch_stride;
+  /* split-KV */
+  int32_t num_splits;          /* 0 = heuristic, 1 = never split, >1 = forced */
+  void* workspace; size_t workspace_bytes;
+  /* debugging: optional fp32 buffer (128x128) receiving the raw S tile of CTA (0,0,0) */
+  float* debug_s;
+} fa_b200_fwd_args;
+
+typedef struct fa_b200_bwd_args {
+  const void* dout; const void* q; const void* k; const void* v; const void* out;
+  const float* softmax_lse;
+  void* dq; void* dk; void* dv;           /* written in place, same layouts as q/k/v */
+  float* softmax_d;                       /* dense (b, h, round128(sq)) | varlen (h, total_q + 128*b) */
+  int64_t q_batch_stride, q_row_stride, q_head_stride;
+  int64_t k_batch_stride, k_row_stride, k_head_stride;
+  int64_t v_batch_stride, v_row_stride, v_head_stride;
+  int64_t o_batch_stride, o_row_stride, o_head_stride;
+  int64_t do_batch_stride, do_row_stride, do_head_stride;
+  int64_t dq_batch_stride, dq_row_stride, dq_head_stride;
+  int64_t dk_batch_stride, dk_row_stride, dk_head_stride;
+  int64_t dv_batch_stride, dv_row_stride, dv_head_stride;
+  int32_t b, seqlen_q, seqlen_k, h, h_k, d;
+  int32_t total_q, total_k;
+  int32_t dtype;
+  const int32_t* cu_seqlens_q; const int32_t* cu_seqlens_k;
+  const float* alibi_slopes; int64_t alibi_slopes_batch_stride;
+  float softmax_scale; float softcap;
+  int32_t is_causal; int32_t window_size_left, window_size_right;
+  int32_t deterministic;
+  void* workspace; size_t workspace_bytes;
+} fa_b200_bwd_args;
+
+/* ---- forward ---- */
+int fa_b200_mha_fwd(const fa_b200_fwd_args* args, fa_b200_stream_t stream);
+int fa_b200_mha_varlen_fwd(const fa_b200_fwd_args* args, fa_b200_stream_t stream);
+int fa_b200_mha_fwd_kvcache(const fa_b200_fwd_args* args, fa_b200_stream_t stream);
+/* bytes of scratch the call will need with these args (0 if it will not split) */
+size_t fa_b200_fwd_workspace_bytes(const fa_b200_fwd_args* args);
+/* the split count the call will use (after heuristic / clamping) */
+int fa_b200_fwd_num_splits(const fa_b200_fwd_args* args);
+
+/* ---- backward ---- */
+int fa_b200_mha_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream);
+int fa_b200_mha_varlen_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream);
+size_t fa_b200_bwd_workspace_bytes(const fa_b200_bwd_args* args);
+
+/* ---- split-KV combine as a standalone op (hopper/flash_api.cpp fwd_combine, flash_attn/cute/interface.py:3687) ----
+ * o_partial (splits, rows, d) fp32, lse_partial (splits, rows) fp32 -> out (rows, d) `dtype`, lse (rows) fp32 */
+int fa_b200_fwd_combine(const float* o_partial, const float* lse_partial, void* out, float* lse,
+                        int32_t num_splits, int64_t rows, int32_t d, int32_t dtype,
+                        fa_b200_stream_t stream);
+
+/* ---- helpers ---- */
+int fa_b200_num_splits_heuristic(int batch_nheads_mblocks, int num_sms, int num_n_blocks, int max_splits);
+const char* fa_b200_last_error(void);
+/* ABI guards for FFI bindings: sizeof the argument structs as compiled into the library */
+size_t fa_b200_sizeof_fwd_args(void);
+size_t fa_b200_sizeof_bwd_args(void);
+const char* fa_b200_version(void);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+uint64_t fa_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */
