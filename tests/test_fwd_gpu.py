@@ -1,0 +1,102 @@
+"""GPU parity tests of the forward path (through the public API -> operator module -> C ABI -> sm_100a
+kernels) against the CPU oracle, with the reference's tolerance rule (tests/util.py)."""
+import math
+
+import pytest
+import torch
+
+from tests.util import check_fwd, make_qkv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fab():
+    import flash_attention_b200 as m
+    from flash_attention_b200 import _lib
+
+    _lib.load()
+    assert torch.cuda.is_available()
+    return m
+
+
+CASES = [
+    # b, sq, sk, h, hk, d, causal, window, softcap, dtype
+    (2, 128, 128, 4, 4, 64, False, (-1, -1), 0.0, torch.bfloat16),   # BASELINE C1 shape (d=64)
+    (2, 128, 128, 4, 4, 64, True, (-1, -1), 0.0, torch.float16),
+    (1, 256, 256, 2, 2, 128, False, (-1, -1), 0.0, torch.bfloat16),
+    (2, 113, 203, 3, 3, 128, False, (-1, -1), 0.0, torch.bfloat16),  # reference seqlen pairs
+    (2, 113, 203, 3, 3, 128, True, (-1, -1), 0.0, torch.bfloat16),
+    (1, 1023, 1024, 2, 1, 128, True, (-1, -1), 0.0, torch.bfloat16),
+    (1, 512, 256, 2, 2, 128, True, (-1, -1), 0.0, torch.float16),    # sq > sk: dead rows
+    (1, 384, 500, 4, 2, 128, False, (100, 37), 0.0, torch.bfloat16),
+    (1, 384, 500, 2, 2, 96, False, (64, -1), 0.0, torch.bfloat16),
+    (1, 700, 700, 1, 1, 128, True, (129, -1), 0.0, torch.bfloat16),
+    (1, 256, 256, 2, 2, 128, False, (-1, -1), 15.0, torch.bfloat16),
+    (2, 1, 777, 8, 1, 128, False, (-1, -1), 0.0, torch.bfloat16),    # decode, packed GQA
+    (2, 5, 260, 16, 2, 128, True, (-1, -1), 0.0, torch.bfloat16),
+    (1, 130, 257, 2, 2, 32, True, (-1, -1), 0.0, torch.bfloat16),
+    (1, 130, 257, 2, 2, 40, False, (-1, -1), 0.0, torch.float16),
+]
+
+
+@pytest.mark.parametrize("b,sq,sk,h,hk,d,causal,window,softcap,dtype", CASES)
+def test_flash_attn_func_matches_oracle(fab, b, sq, sk, h, hk, d, causal, window, softcap, dtype):
+    q, k, v = make_qkv(b, sq, sk, h, hk, d, dtype)
+    out, lse, _ = fab.flash_attn_func(q, k, v, causal=causal, window_size=window, softcap=softcap, return_attn_probs=True)
+    check_fwd(out, lse, q, k, v, causal=causal, window=window, softcap=softcap)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("per_batch", [False, True])
+def test_alibi(fab, causal, per_batch):
+    b, sq, sk, h = 2, 200, 333, 4
+    q, k, v = make_qkv(b, sq, sk, h, h, 128)
+    sl = (torch.rand((b, h) if per_batch else (h,), device="cuda") * 0.3).float()
+    out, lse, _ = fab.flash_attn_func(q, k, v, causal=causal, alibi_slopes=sl, return_attn_probs=True)
+    check_fwd(out, lse, q, k, v, causal=causal, alibi_slopes=sl)
+
+
+def test_strided_inputs_and_out_layout(fab):
+    """qkv-packed views: non-contiguous row/head strides go straight into the TMA descriptors."""
+    b, s, h, d = 2, 300, 4, 128
+    qkv = torch.randn(b, s, 3, h, d, device="cuda", dtype=torch.bfloat16)
+    out = fab.flash_attn_qkvpacked_func(qkv, causal=True)
+    check_fwd(out, None, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=True)
+
+
+def test_empty_keys_gives_zero_out_inf_lse(fab):
+    q, k, v = make_qkv(1, 64, 0, 2, 2, 128)
+    out, lse, _ = fab.flash_attn_func(q, k, v, return_attn_probs=True)
+    assert torch.all(out == 0) and torch.all(torch.isinf(lse) & (lse > 0))
+
+
+def test_error_messages(fab):
+    q, k, v = make_qkv(1, 64, 64, 3, 2, 128)
+    with pytest.raises(RuntimeError, match="must divide"):
+        fab.flash_attn_func(q, k, v)
+    q, k, v = make_qkv(1, 64, 64, 2, 2, 128, torch.float32)
+    with pytest.raises(RuntimeError, match="fp16 and bf16"):
+        fab.flash_attn_func(q, k, v)
+
+
+def test_key_permutation_invariance_full_size(fab):
+    """Size-independent property at a BASELINE-scale shape (non-causal): permuting keys/values together
+    leaves the output unchanged up to accumulation order; compared on the device."""
+    q, k, v = make_qkv(1, 2048, 8192, 4, 4, 128)
+    perm = torch.randperm(8192, device="cuda")
+    o1 = fab.flash_attn_func(q, k, v)
+    o2 = fab.flash_attn_func(q, k[:, perm], v[:, perm])
+    assert (o1.float() - o2.float()).abs().max().item() < 4e-3
+
+
+def test_full_size_rows_vs_oracle(fab):
+    """BASELINE C2 shape (b4 h16 s8192 d128), oracle evaluated on a slice: last 256 query rows of one
+    (batch, head) against all 8192 keys (bottom-right aligned => valid for causal too)."""
+    b, h, s, d = 4, 16, 8192, 128
+    q, k, v = make_qkv(b, s, s, h, h, d, seed=1)
+    for causal in (False, True):
+        out, lse, _ = fab.flash_attn_func(q, k, v, causal=causal, return_attn_probs=True)
+        bi, hi = 3, 11
+        check_fwd(out[bi:bi + 1, -256:, hi:hi + 1], lse[bi:bi + 1, hi:hi + 1, -256:], q[bi:bi + 1, -256:, hi:hi + 1],
+                  k[bi:bi + 1, :, hi:hi + 1], v[bi:bi + 1, :, hi:hi + 1], causal=causal)
