@@ -1,9 +1,165 @@
-// fa_bwd_api.cu — backward entry points (placeholder until the sm_100a backward kernels land).
+// fa_bwd_api.cu — C-ABI host layer for the backward pass (restates mha_bwd / mha_varlen_bwd,
+// csrc/flash_attn/flash_api.cpp:800-1241, for the sm_100a kernels in fa_bwd_sm100.cuh).
+//
+// Differences from the reference host code, by design:
+//   * GQA: dK/dV of a KV head are accumulated over its g query heads inside the kernel (TMEM), so there
+//     are no (b, sk, h, d) dk_expanded/dv_expanded temporaries and no at::sum_out (flash_api.cpp:935-942,1002-1005).
+//   * dq_accum is laid out (b, h, round128(max_sq), kD) so that one TMA box = one 128-row dQ tile.
+#include <cstring>
+
 #include "../../include/fa_b200.h"
 #include "fa_api_common.h"
+#include "fa_bwd_sm100.cuh"
+
+namespace fa {
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct BwdPlan {
+  int kD, sq_r;
+  int has_left, has_right, wl, wr;
+  size_t off_lse, off_dps, off_dq, total;
+};
+
+static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
+  if (a.dtype != FA_B200_FP16 && a.dtype != FA_B200_BF16) return set_error("FlashAttention only support fp16 and bf16 data type");
+  if (!a.dout || !a.q || !a.k || !a.v || !a.out || !a.softmax_lse || !a.dq || !a.dk || !a.dv)
+    return set_error("dout, q, k, v, out, softmax_lse, dq, dk, dv must be non-null");
+  if (a.b <= 0) return set_error("batch size must be positive");
+  if (a.d <= 0 || a.d > 256) return set_error("FlashAttention backward only supports head dimension at most 256");
+  if (a.d % 8 != 0) return set_error("head_size should be a multiple of 8");
+  if (a.d > 128) return set_error("this build of fa_b200 supports head dimension at most 128");
+  if (a.h <= 0 || a.h_k <= 0 || a.h % a.h_k != 0)
+    return set_error("Number of heads in key/value must divide number of heads in query");
+  if (varlen && (!a.cu_seqlens_q || !a.cu_seqlens_k)) return set_error("cu_seqlens_q and cu_seqlens_k are required");
+  pl->kD = a.d <= 64 ? 64 : 128;
+  pl->sq_r = (a.seqlen_q + 127) / 128 * 128;
+  int wl = a.window_size_left, wr = a.window_size_right;
+  if (wl >= a.seqlen_k) wl = -1;
+  if (wr >= a.seqlen_k) wr = -1;
+  if (a.is_causal) wr = 0;
+  pl->has_left = wl >= 0; pl->has_right = wr >= 0; pl->wl = wl; pl->wr = wr;
+  const size_t stat = size_t(a.b) * a.h * pl->sq_r * sizeof(float);
+  pl->off_lse = 0;
+  pl->off_dps = align256(stat);
+  pl->off_dq = pl->off_dps + align256(stat);
+  pl->total = pl->off_dq + align256(stat * pl->kD);
+  return 0;
+}
+
+template <typename T, int kD, bool kSoftcap>
+static int launch_bwd_main(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+  using Cfg = BwdCfg<kD>;
+  static bool configured = false;
+  auto kern = fa_bwd_kernel<T, kD, kSoftcap>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(bwd): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_bwd_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+template <typename T, int kD>
+static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varlen, cudaStream_t stream) {
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a.workspace);
+  float* lse_log2 = reinterpret_cast<float*>(ws + pl.off_lse);
+  float* dpsum = reinterpret_cast<float*>(ws + pl.off_dps);
+  float* dq_accum = reinterpret_cast<float*>(ws + pl.off_dq);
+  const int sq_r = pl.sq_r;
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, size_t(a.b) * a.h * sq_r * kD * sizeof(float), stream);
+  if (e != cudaSuccess) return set_error(std::string("cudaMemsetAsync(dq_accum): ") + cudaGetErrorString(e));
+  {
+    dim3 grid((sq_r + 7) / 8, a.h, a.b);
+    fa_bwd_preprocess<T><<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const T*>(a.out), reinterpret_cast<const T*>(a.dout), a.softmax_lse, dpsum, lse_log2, a.softmax_d,
+        a.o_batch_stride, a.o_row_stride, a.o_head_stride, a.do_batch_stride, a.do_row_stride, a.do_head_stride,
+        a.cu_seqlens_q, a.b, a.h, a.seqlen_q, sq_r, a.d, a.total_q);
+    g_launch_count++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return set_error(std::string("fa_bwd_preprocess launch: ") + cudaGetErrorString(e));
+  }
+  BwdKernelParams kp;
+  memset(&kp, 0, sizeof kp);
+  const CUtensorMapDataType dt = a.dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  auto map16 = [&](CUtensorMap* tm, const void* base, int64_t bs, int64_t rs, int64_t hs, int rows_dense, int rows_varlen,
+                   int heads) -> int {
+    uint64_t rows = varlen ? rows_varlen : rows_dense, nb = varlen ? 1 : a.b;
+    uint64_t dims[4] = {uint64_t(a.d), rows, uint64_t(heads), nb};
+    uint64_t str[3] = {uint64_t(rs) * 2, uint64_t(hs) * 2, uint64_t(bs) * 2};
+    if (nb == 1) str[2] = rows * str[0];
+    uint32_t box[4] = {64, 128, 1, 1};
+    return make_tmap(tm, dt, 4, base, dims, str, box);
+  };
+  if (int rc = map16(&kp.tm_q, a.q, a.q_batch_stride, a.q_row_stride, a.q_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
+  if (int rc = map16(&kp.tm_do, a.dout, a.do_batch_stride, a.do_row_stride, a.do_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
+  if (int rc = map16(&kp.tm_k, a.k, a.k_batch_stride, a.k_row_stride, a.k_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
+  if (int rc = map16(&kp.tm_v, a.v, a.v_batch_stride, a.v_row_stride, a.v_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
+  {
+    uint64_t dims[4] = {uint64_t(kD), uint64_t(sq_r), uint64_t(a.h), uint64_t(a.b)};
+    uint64_t str[3] = {uint64_t(kD) * 4, uint64_t(sq_r) * kD * 4, uint64_t(a.h) * sq_r * kD * 4};
+    uint32_t box[4] = {32, 128, 1, 1};
+    if (int rc = make_tmap(&kp.tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, dims, str, box)) return rc;
+  }
+  kp.lse_log2 = lse_log2;
+  kp.dpsum = dpsum;
+  kp.dk = a.dk; kp.dv = a.dv;
+  kp.dk_batch_stride = a.dk_batch_stride; kp.dk_row_stride = a.dk_row_stride; kp.dk_head_stride = a.dk_head_stride;
+  kp.dv_batch_stride = a.dv_batch_stride; kp.dv_row_stride = a.dv_row_stride; kp.dv_head_stride = a.dv_head_stride;
+  kp.cu_seqlens_q = a.cu_seqlens_q; kp.cu_seqlens_k = a.cu_seqlens_k;
+  kp.alibi_slopes = a.alibi_slopes; kp.alibi_batch_stride = a.alibi_slopes_batch_stride;
+  kp.b = a.b; kp.h = a.h; kp.h_k = a.h_k; kp.sq = a.seqlen_q; kp.sk = a.seqlen_k; kp.d = a.d; kp.g = a.h / a.h_k;
+  kp.sq_r = sq_r;
+  kp.has_left = pl.has_left; kp.has_right = pl.has_right; kp.wl = pl.wl; kp.wr = pl.wr;
+  kp.scale = a.softmax_scale;
+  if (a.softcap > 0.f) { kp.softcap_pre = a.softmax_scale / a.softcap; kp.scale_eff = a.softcap; }
+  else { kp.softcap_pre = 0.f; kp.scale_eff = a.softmax_scale; }
+  kp.scale_log2 = kp.scale_eff * float(M_LOG2E);
+  dim3 grid((a.seqlen_k + 127) / 128, a.h_k, a.b);
+  int rc = a.softcap > 0.f ? launch_bwd_main<T, kD, true>(kp, grid, stream) : launch_bwd_main<T, kD, false>(kp, grid, stream);
+  if (rc) return rc;
+  {
+    dim3 cgrid((a.seqlen_q + 7) / 8, a.h, a.b);
+    fa_bwd_convert_dq<T, kD><<<cgrid, 256, 0, stream>>>(dq_accum, reinterpret_cast<T*>(a.dq), a.dq_batch_stride, a.dq_row_stride,
+                                                      a.dq_head_stride, a.cu_seqlens_q, a.h, a.seqlen_q, sq_r, a.d,
+                                                      a.softmax_scale);
+    g_launch_count++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return set_error(std::string("fa_bwd_convert_dq launch: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+static int run_bwd(const fa_b200_bwd_args& a, bool varlen, cudaStream_t stream) {
+  BwdPlan pl;
+  if (int rc = plan_bwd(a, varlen, &pl)) return rc;
+  if (!a.workspace || a.workspace_bytes < pl.total) return set_error("workspace too small for backward (query fa_b200_bwd_workspace_bytes)");
+  if (reinterpret_cast<uintptr_t>(a.workspace) % 256 != 0) return set_error("backward workspace must be 256-byte aligned");
+  if (a.seqlen_q == 0 || a.seqlen_k == 0) return 0;
+  if (a.dtype == FA_B200_BF16)
+    return pl.kD == 64 ? run_bwd_typed<__nv_bfloat16, 64>(a, pl, varlen, stream) : run_bwd_typed<__nv_bfloat16, 128>(a, pl, varlen, stream);
+  return pl.kD == 64 ? run_bwd_typed<__half, 64>(a, pl, varlen, stream) : run_bwd_typed<__half, 128>(a, pl, varlen, stream);
+}
+
+}  // namespace fa
+
+using namespace fa;
 
 extern "C" {
-int fa_b200_mha_bwd(const fa_b200_bwd_args*, fa_b200_stream_t) { return fa::set_error("fa_b200 backward is not built in this revision"); }
-int fa_b200_mha_varlen_bwd(const fa_b200_bwd_args*, fa_b200_stream_t) { return fa::set_error("fa_b200 backward is not built in this revision"); }
-size_t fa_b200_bwd_workspace_bytes(const fa_b200_bwd_args*) { return 0; }
+int fa_b200_mha_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream) {
+  if (!args) return set_error("null args");
+  if (args->cu_seqlens_q || args->cu_seqlens_k) return set_error("fa_b200_mha_bwd takes dense tensors; use fa_b200_mha_varlen_bwd");
+  return run_bwd(*args, false, static_cast<cudaStream_t>(stream));
+}
+int fa_b200_mha_varlen_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream) {
+  if (!args) return set_error("null args");
+  return run_bwd(*args, true, static_cast<cudaStream_t>(stream));
+}
+size_t fa_b200_bwd_workspace_bytes(const fa_b200_bwd_args* args) {
+  BwdPlan pl;
+  if (!args || plan_bwd(*args, args->cu_seqlens_q != nullptr, &pl)) return 0;
+  return pl.total;
+}
 }

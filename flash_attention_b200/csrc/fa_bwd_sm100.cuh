@@ -1,0 +1,525 @@
+// fa_bwd_sm100.cuh — backward attention (dQ, dK, dV) for sm_100a (B200).
+//
+// Three kernels (the reference's split, flash_bwd_launch_template.h:72-126):
+//   fa_bwd_preprocess  D = rowsum(dO * O), lse_log2 = LSE * log2(e)          (flash_bwd_preprocess_kernel.h:57-140)
+//   fa_bwd_kernel      per 128-key block: loop over the 128-query blocks (and over the g query heads of a
+//                      GQA group) recomputing P and accumulating dK, dV in TMEM; dQ partials are
+//                      TMA-reduce-added into an fp32 accumulator                 (flash_bwd_kernel.h:80-795)
+//   fa_bwd_convert_dq  dq = T(dq_accum * softmax_scale)                          (flash_bwd_preprocess_kernel.h:185-268)
+//
+// Main loop, everything transposed so that the resident K/V block is the MMA M operand (TMEM lane = key):
+//   S^T  = K Q^T            SS   -> TMEM [0,128)
+//   dP^T = V dO^T           SS   -> TMEM [128,256)
+//   P^T  = exp2(S^T*c - lse_log2[q])      compute warps, fp32 -> 16-bit into TMEM [0,64)
+//   dS^T = P^T * (dP^T - D[q])            compute warps -> TMEM [64,128) and shared memory (swizzled)
+//   dV  += P^T dO           TS   -> TMEM [256,384)      (A = P^T from TMEM, B = dO as MN-major)
+//   dK  += dS^T Q           TS   -> TMEM [384,512)
+//   dQ   = dS K             SS   -> TMEM [128,256)      (A = dS^T tile as MN-major, B = K as MN-major)
+//   dQ -> registers -> swizzled smem -> cp.reduce.async.bulk.tensor (fp32 add) into dq_accum
+//
+// Warps (512 threads, 4 warpgroups): 0-7 compute (warp w: key rows 32*(w%4).., query half w/4),
+// 8-11 dQ drain, 12 MMA issuer, 13 TMA producer.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "fa_fwd_sm100.cuh"
+#include "fa_ptx.cuh"
+
+namespace fa {
+
+struct BwdKernelParams {
+  CUtensorMap tm_q, tm_do;   // 4-D (d, rows, h, b)    box (64, 128, 1, 1)  16-bit
+  CUtensorMap tm_k, tm_v;    // 4-D (d, rows, h_k, b)
+  CUtensorMap tm_dq;         // 4-D (kD, sq_r, h, b) fp32, box (32, 128, 1, 1), 128B swizzle, reduce-add target
+  const float* lse_log2;     // (b, h, sq_r)
+  const float* dpsum;        // (b, h, sq_r)
+  void* dk;
+  void* dv;
+  int64_t dk_batch_stride, dk_row_stride, dk_head_stride;
+  int64_t dv_batch_stride, dv_row_stride, dv_head_stride;
+  const int* cu_seqlens_q;
+  const int* cu_seqlens_k;
+  const float* alibi_slopes;
+  int64_t alibi_batch_stride;
+  int b, h, h_k, sq, sk, d, g;
+  int sq_r;                  // round128(max seqlen_q): row pitch of lse_log2 / dpsum / dq_accum
+  int has_right, has_left, wl, wr;
+  float scale;               // softmax_scale: dK is multiplied by it in the epilogue (dQ in the convert kernel)
+  float scale_eff;           // scale of the logits inside exp: softcap if softcap > 0 else softmax_scale
+  float scale_log2;          // scale_eff * log2(e)
+  float softcap_pre;
+};
+
+template <int kD>
+struct BwdCfg {
+  static constexpr int kThreads = 512;
+  static constexpr int kPanels = kD / 64;
+  static constexpr int kPanelBytes = 128 * 128;
+  static constexpr int kTileBytes = kPanels * kPanelBytes;   // one 128-row 16-bit tile
+  static constexpr int kSK = 0;
+  static constexpr int kSV = kSK + kTileBytes;
+  static constexpr int kSQ = kSV + kTileBytes;               // 2 stages
+  static constexpr int kSDO = kSQ + 2 * kTileBytes;
+  static constexpr int kSDS = kSDO + kTileBytes;             // 128 keys x 128 queries, 16-bit, two 64-query panels
+  static constexpr int kSDQ = kSDS + 2 * kPanelBytes;        // 2 staging buffers of 128 rows x 32 fp32
+  static constexpr int kSStat = kSDQ + 2 * kPanelBytes;      // lse_log2[2][128], dpsum[2][128]
+  static constexpr int kSBar = kSStat + 4 * 512;
+  static constexpr int kNumBars = 16;
+  static constexpr int kSmemBytes = kSBar + 8 * kNumBars + 16;  // dynamic smem is declared 1024-aligned
+};
+
+// ---------------------------------------------------------------------------------------------- preprocess
+// one warp per query row: D = sum_d dO*O ; lse_log2 = lse*log2e (+inf on padding rows so that P == 0 there)
+template <typename T>
+__global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o, const T* __restrict__ dout,
+                                                         const float* __restrict__ lse, float* __restrict__ dpsum,
+                                                         float* __restrict__ lse_log2, float* __restrict__ softmax_d,
+                                                         int64_t o_bs, int64_t o_rs, int64_t o_hs, int64_t do_bs,
+                                                         int64_t do_rs, int64_t do_hs, const int* __restrict__ cu_q,
+                                                         int b, int h, int sq, int sq_r, int d, int total_q) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;  // in [0, sq_r)
+  const int head = blockIdx.y, bidb = blockIdx.z;
+  if (row >= sq_r) return;
+  int q_off = 0, sq_b = sq;
+  if (cu_q) { q_off = cu_q[bidb]; sq_b = cu_q[bidb + 1] - q_off; }
+  const int64_t sidx = (int64_t(bidb) * h + head) * sq_r + row;
+  float acc = 0.f, l2 = INFINITY;
+  if (row < sq_b) {
+    const T* po = o + (cu_q ? 0 : bidb * o_bs) + int64_t(q_off + row) * o_rs + int64_t(head) * o_hs;
+    const T* pd = dout + (cu_q ? 0 : bidb * do_bs) + int64_t(q_off + row) * do_rs + int64_t(head) * do_hs;
+    for (int c = lane * 4; c < d; c += 128) {
+      const uint2 a = *reinterpret_cast<const uint2*>(po + c);
+      const uint2 g = *reinterpret_cast<const uint2*>(pd + c);
+      const T* av = reinterpret_cast<const T*>(&a);
+      const T* gv = reinterpret_cast<const T*>(&g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc += float(av[e]) * float(gv[e]);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    const float l = cu_q ? lse[int64_t(head) * total_q + q_off + row] : lse[(int64_t(bidb) * h + head) * sq + row];
+    l2 = l * 1.4426950408889634f;  // +inf stays +inf (fully masked row), -inf cannot occur for non-split forward
+  }
+  if (lane == 0) {
+    dpsum[sidx] = acc;
+    lse_log2[sidx] = l2;
+    // API-visible softmax_d in the reference layouts: dense (b,h,sq_r) | varlen (h, total_q + 128*b)
+    if (softmax_d) {
+      if (cu_q) { if (row < sq_b || row < ((sq_b + 127) / 128) * 128) softmax_d[int64_t(head) * (total_q + 128 * b) + q_off + 128 * bidb + row] = acc; }
+      else softmax_d[sidx] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- dq convert
+template <typename T, int kD>
+__global__ void __launch_bounds__(256) fa_bwd_convert_dq(const float* __restrict__ dq_accum, T* __restrict__ dq,
+                                                         int64_t dq_bs, int64_t dq_rs, int64_t dq_hs,
+                                                         const int* __restrict__ cu_q, int h, int sq, int sq_r, int d,
+                                                         float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int head = blockIdx.y, bidb = blockIdx.z;
+  int q_off = 0, sq_b = sq;
+  if (cu_q) { q_off = cu_q[bidb]; sq_b = cu_q[bidb + 1] - q_off; }
+  if (row >= sq_b) return;
+  const float* src = dq_accum + ((int64_t(bidb) * h + head) * sq_r + row) * kD;
+  T* dst = dq + (cu_q ? 0 : bidb * dq_bs) + int64_t(q_off + row) * dq_rs + int64_t(head) * dq_hs;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    uint2 o;
+    o.x = Elt<T>::pack(v.x * scale, v.y * scale);
+    o.y = Elt<T>::pack(v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(dst + c) = o;
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+template <typename T, int kD, bool kSoftcap>
+__global__ void __launch_bounds__(BwdCfg<kD>::kThreads, 1)
+fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
+  using Cfg = BwdCfg<kD>;
+  constexpr float kNegInf = -INFINITY;
+  const int n_block = blockIdx.x, hk = blockIdx.y, bidb = blockIdx.z;
+  int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
+  if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
+  if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
+  const int key0 = n_block * 128;
+  if (key0 >= sk_b) return;
+  const int shift = sk_b - sq_b;
+  const int m_total = (sq_b + 127) / 128;
+  int m_min = 0, m_max = m_total;
+  if (p.has_right) {  // query i sees key j iff j <= i + shift + wr  ->  i >= j - shift - wr
+    int lo = key0 - shift - p.wr;
+    m_min = lo <= 0 ? 0 : lo / 128;
+  }
+  if (p.has_left) {   // j >= i + shift - wl  ->  i <= j - shift + wl
+    int hi = key0 + 127 - shift + p.wl;  // last query that can see the last key of the block
+    int nb = hi < 0 ? 0 : hi / 128 + 1;
+    m_max = nb < m_max ? nb : m_max;
+  }
+  const int n_m = m_max > m_min ? m_max - m_min : 0;
+  const int n_iter = n_m * p.g;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();  // the 128B-swizzle atoms need 1024-byte aligned tiles
+  uint8_t* smem_gen = smem_raw;
+  const uint32_t sK = smem_base + Cfg::kSK, sV = smem_base + Cfg::kSV, sQ = smem_base + Cfg::kSQ;
+  const uint32_t sDO = smem_base + Cfg::kSDO, sDS = smem_base + Cfg::kSDS, sDQ = smem_base + Cfg::kSDQ;
+  const uint32_t sStat = smem_base + Cfg::kSStat, sBar = smem_base + Cfg::kSBar;
+  enum { B_KV = 0, B_QF0 = 1, B_QF1 = 2, B_QE0 = 3, B_QE1 = 4, B_DOF = 5, B_DOE = 6, B_SF = 7, B_DPF = 8, B_PF = 9,
+         B_DSF = 10, B_DQF = 11, B_DQE = 12, B_DKV = 13 };
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSBar + 8 * Cfg::kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_do); tma_prefetch_desc(&p.tm_k);
+    tma_prefetch_desc(&p.tm_v); tma_prefetch_desc(&p.tm_dq);
+  }
+  if (warp == 12) {
+    if (lane == 0) {
+      mbar_init(bar(B_KV), 1);
+      mbar_init(bar(B_QF0), 1); mbar_init(bar(B_QF1), 1);
+      mbar_init(bar(B_QE0), 1); mbar_init(bar(B_QE1), 1);
+      mbar_init(bar(B_DOF), 1); mbar_init(bar(B_DOE), 1);
+      mbar_init(bar(B_SF), 1); mbar_init(bar(B_DPF), 1);
+      mbar_init(bar(B_PF), 8); mbar_init(bar(B_DSF), 8);
+      mbar_init(bar(B_DQF), 1); mbar_init(bar(B_DQE), 4);
+      mbar_init(bar(B_DKV), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(sTmemPtr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 384;
+
+  if (warp >= 12) {
+    reg_dealloc<40>();
+    // ================================================================ TMA producer
+    if (warp == 13) {
+      if (lane == 0) {
+        const int bk = p.cu_seqlens_k ? 0 : bidb, bq = p.cu_seqlens_q ? 0 : bidb;
+        mbar_arrive_expect_tx(bar(B_KV), 2 * Cfg::kTileBytes);
+#pragma unroll
+        for (int pn = 0; pn < Cfg::kPanels; ++pn) {
+          tma_load_4d(sK + pn * Cfg::kPanelBytes, &p.tm_k, bar(B_KV), pn * 64, k_off + key0, hk, bk);
+          tma_load_4d(sV + pn * Cfg::kPanelBytes, &p.tm_v, bar(B_KV), pn * 64, k_off + key0, hk, bk);
+        }
+        for (int it = 0; it < n_iter; ++it) {
+          const int hq = hk * p.g + it / n_m;
+          const int m = m_min + it % n_m;
+          const int st = it & 1;
+          const int64_t srow = (int64_t(bidb) * p.h + hq) * p.sq_r + m * 128;
+          mbar_wait(bar(B_QE0 + st), ((it >> 1) & 1) ^ 1, 400 + st);
+          mbar_arrive_expect_tx(bar(B_QF0 + st), Cfg::kTileBytes + 1024);
+#pragma unroll
+          for (int pn = 0; pn < Cfg::kPanels; ++pn)
+            tma_load_4d(sQ + st * Cfg::kTileBytes + pn * Cfg::kPanelBytes, &p.tm_q, bar(B_QF0 + st), pn * 64,
+                        q_off + m * 128, hq, bq);
+          bulk_load_1d(sStat + st * 512, p.lse_log2 + srow, 512, bar(B_QF0 + st));
+          bulk_load_1d(sStat + 1024 + st * 512, p.dpsum + srow, 512, bar(B_QF0 + st));
+          mbar_wait(bar(B_DOE), (it & 1) ^ 1, 410);
+          mbar_arrive_expect_tx(bar(B_DOF), Cfg::kTileBytes);
+#pragma unroll
+          for (int pn = 0; pn < Cfg::kPanels; ++pn)
+            tma_load_4d(sDO + pn * Cfg::kPanelBytes, &p.tm_do, bar(B_DOF), pn * 64, q_off + m * 128, hq, bq);
+        }
+      }
+      __syncwarp();
+    }
+    // ================================================================ MMA issuer
+    else if (warp == 12) {
+      if (n_iter > 0) {
+        constexpr uint32_t fmt = Elt<T>::kFmt;
+        constexpr uint32_t id_s = make_idesc(fmt, fmt, 0, 0, 128, 128);    // S^T, dP^T : K-major A and B
+        constexpr uint32_t id_dkv = make_idesc(fmt, fmt, 0, 1, 128, kD);   // dV, dK   : A in TMEM, B MN-major
+        constexpr uint32_t id_dq = make_idesc(fmt, fmt, 1, 1, 128, kD);    // dQ       : A and B MN-major
+        constexpr uint64_t dk_major = smem_desc_sw128(16, 1024);
+        constexpr uint64_t dmn_major = smem_desc_sw128(Cfg::kPanelBytes, 1024);
+        auto mma_kmajor = [&](uint32_t d_t, uint32_t a0, uint32_t b0, uint32_t idesc) {
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t off = (kk / 4) * Cfg::kPanelBytes + (kk % 4) * 32;
+            mma_ss<false>(d_t, smem_desc_at(dk_major, a0 + off), smem_desc_at(dk_major, b0 + off), idesc, kk > 0);
+          }
+        };
+        auto mma_ts_mn = [&](uint32_t d_t, uint32_t a_t, uint32_t b0, bool acc) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ts<false>(d_t, a_t + kk * 8, smem_desc_at(dmn_major, b0 + kk * 2048), id_dkv, (acc || kk > 0) ? 1u : 0u);
+        };
+        mbar_wait(bar(B_KV), 0, 500);
+        mbar_wait(bar(B_QF0), 0, 501);
+        tc_fence_after();
+        if (lane == 0) { mma_kmajor(tS, sK, sQ, id_s); mma_commit(bar(B_SF)); }
+        mbar_wait(bar(B_DOF), 0, 502);
+        tc_fence_after();
+        if (lane == 0) { mma_kmajor(tDP, sV, sDO, id_s); mma_commit(bar(B_DPF)); }
+        __syncwarp();
+        for (int it = 0; it < n_iter; ++it) {
+          const int st = it & 1;
+          const uint32_t ph = it & 1;
+          mbar_wait(bar(B_PF), ph, 510);
+          tc_fence_after();
+          if (lane == 0) {
+            mma_ts_mn(tDV, tS, sDO, it > 0);
+            mma_commit(bar(B_DOE));
+          }
+          mbar_wait(bar(B_DSF), ph, 511);
+          tc_fence_after();
+          if (lane == 0) {
+            mma_ts_mn(tDK, tS + 64, sQ + st * Cfg::kTileBytes, it > 0);
+            mma_commit(bar(B_QE0 + st));
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              mma_ss<false>(tDP, smem_desc_at(dmn_major, sDS + kk * 2048), smem_desc_at(dmn_major, sK + kk * 2048), id_dq,
+                            kk > 0);
+            mma_commit(bar(B_DQF));
+          }
+          if (it + 1 < n_iter) {
+            const int st1 = st ^ 1;
+            mbar_wait(bar(B_QF0 + st1), ((it + 1) >> 1) & 1, 512);
+            tc_fence_after();
+            if (lane == 0) { mma_kmajor(tS, sK, sQ + st1 * Cfg::kTileBytes, id_s); mma_commit(bar(B_SF)); }
+            mbar_wait(bar(B_DQE), ph, 513);           // dQ_it drained out of TMEM [128,256)
+            mbar_wait(bar(B_DOF), (it + 1) & 1, 514);
+            tc_fence_after();
+            if (lane == 0) { mma_kmajor(tDP, sV, sDO, id_s); mma_commit(bar(B_DPF)); }
+          }
+          __syncwarp();
+        }
+        if (lane == 0) mma_commit(bar(B_DKV));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // ================================================================ dQ drain: TMEM -> smem -> TMA reduce-add
+    reg_alloc<152>();
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;  // query row within the block
+    const uint32_t t_dq = tDP + (uint32_t(wq * 32) << 16);
+    const bool leader = (warp == 8 && lane == 0);
+    int nbuf = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int hq = hk * p.g + it / n_m;
+      const int m = m_min + it % n_m;
+      mbar_wait(bar(B_DQF), it & 1, 600);
+      tc_fence_after();
+      uint32_t v[kD];
+#pragma unroll
+      for (int cc = 0; cc < kD; cc += 32) tmem_ld_x32(t_dq + cc, v + cc);
+      tmem_wait_ld();
+      // everything is in registers: hand TMEM [128,256) back to the MMA warp (next dP^T)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_DQE));
+#pragma unroll
+      for (int c = 0; c < kD / 32; ++c, ++nbuf) {
+        const int buf = nbuf & 1;
+        // the TMA reduce that last read this staging buffer must have finished reading it
+        if (leader && nbuf >= 2) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint8_t* dst = smem_gen + Cfg::kSDQ + buf * Cfg::kPanelBytes + r * 128;
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+          *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) =
+              make_uint4(v[c * 32 + 4 * x], v[c * 32 + 4 * x + 1], v[c * 32 + 4 * x + 2], v[c * 32 + 4 * x + 3]);
+        fence_proxy_async();
+        named_bar_sync(2, 128);
+        if (leader) {
+          tma_reduce_add_4d(&p.tm_dq, sDQ + buf * Cfg::kPanelBytes, c * 32, m * 128, hq, bidb);
+          tma_store_commit();
+        }
+      }
+    }
+    if (leader) tma_store_wait<0>();
+  } else {
+    // ================================================================ compute warps
+    reg_alloc<160>();
+    const int wq = warp & 3, hf = warp >> 2;          // key-row quadrant, query half
+    const int r = wq * 32 + lane;                       // key row within the block
+    const int j = key0 + r;                             // key index in the sequence
+    const uint32_t lane_sel = uint32_t(wq * 32) << 16;
+    const uint32_t t_s = tS + lane_sel + hf * 64;       // my 64 S^T columns
+    const uint32_t t_dp = tDP + lane_sel + hf * 64;
+    const uint32_t t_p = tS + lane_sel + hf * 32;       // P^T  packed: 32 columns
+    const uint32_t t_ds = tS + lane_sel + 64 + hf * 32; // dS^T packed
+    const float scale_log2 = p.scale_log2;
+    // visible queries for this key: i in [i_lo, i_hi]
+    const int i_lo = p.has_right ? j - shift - p.wr : -(1 << 30);
+    const int i_hi = p.has_left ? j - shift + p.wl : (1 << 30);
+    const bool key_valid = j < sk_b;
+    for (int it = 0; it < n_iter; ++it) {
+      const int hq = hk * p.g + it / n_m;
+      const int m = m_min + it % n_m;
+      const int st = it & 1;
+      const int q0 = m * 128 + hf * 64;  // first query of my half
+      float slope = 0.f;
+      if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + hq] / p.scale_eff;
+      mbar_wait(bar(B_QF0 + st), (it >> 1) & 1, 700);   // lse/dpsum of this stage are in smem
+      mbar_wait(bar(B_SF), it & 1, 701);
+      tc_fence_after();
+      uint32_t su[64];
+      tmem_ld_x32(t_s, su);
+      tmem_ld_x32(t_s + 32, su + 32);
+      tmem_wait_ld();
+      float* s = reinterpret_cast<float*>(su);
+      const float* s_lse = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + st * 512) + hf * 64;
+      const float* s_dps = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + 1024 + st * 512) + hf * 64;
+      const float rel0 = float(q0 + shift - j);
+      if constexpr (kSoftcap) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = tanh_approx(s[c] * p.softcap_pre);
+      }
+      if (p.alibi_slopes) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = fmaf(-slope, fabsf(rel0 + float(c)), s[c]);
+      }
+      bool need_mask = key0 + 127 >= sk_b;
+      if (p.has_right) need_mask |= key0 + 127 > m * 128 + shift + p.wr;
+      if (p.has_left) need_mask |= key0 < m * 128 + 127 + shift - p.wl;
+      // ---- phase 1: P^T = exp2(S^T * c - lse_log2[q])
+      float pr[64];
+#pragma unroll
+      for (int c4 = 0; c4 < 64; c4 += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_lse + c4);
+        pr[c4 + 0] = ex2(fmaf(s[c4 + 0], scale_log2, -l4.x));
+        pr[c4 + 1] = ex2(fmaf(s[c4 + 1], scale_log2, -l4.y));
+        pr[c4 + 2] = ex2(fmaf(s[c4 + 2], scale_log2, -l4.z));
+        pr[c4 + 3] = ex2(fmaf(s[c4 + 3], scale_log2, -l4.w));
+      }
+      if (need_mask) {
+        const int lo = i_lo - q0, hi = i_hi - q0;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) pr[c] = (!key_valid || c < lo || c > hi) ? 0.f : pr[c];
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) pk[c / 2] = Elt<T>::pack(pr[c], pr[c + 1]);
+        tmem_st_x32(t_p, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_PF));
+      }
+      // ---- phase 2: dS^T = P^T * (dP^T - D[q])  (* (1 - tanh^2) with softcap)
+      mbar_wait(bar(B_DPF), it & 1, 702);
+      tc_fence_after();
+      uint32_t dk_[32];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t du[32];
+        tmem_ld_x32(t_dp + h2 * 32, du);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c4 = 0; c4 < 32; c4 += 4) {
+          const int cc = h2 * 32 + c4;
+          const float4 d4 = *reinterpret_cast<const float4*>(s_dps + cc);
+          float e0 = pr[cc + 0] * (__uint_as_float(du[c4 + 0]) - d4.x);
+          float e1 = pr[cc + 1] * (__uint_as_float(du[c4 + 1]) - d4.y);
+          float e2 = pr[cc + 2] * (__uint_as_float(du[c4 + 2]) - d4.z);
+          float e3 = pr[cc + 3] * (__uint_as_float(du[c4 + 3]) - d4.w);
+          if constexpr (kSoftcap) {  // d tanh(x) = 1 - tanh^2 (utils.h:403-409); undo the ALiBi bias first
+            float t0 = s[cc + 0], t1 = s[cc + 1], t2 = s[cc + 2], t3 = s[cc + 3];
+            if (p.alibi_slopes) {
+              t0 = fmaf(slope, fabsf(rel0 + float(cc + 0)), t0);
+              t1 = fmaf(slope, fabsf(rel0 + float(cc + 1)), t1);
+              t2 = fmaf(slope, fabsf(rel0 + float(cc + 2)), t2);
+              t3 = fmaf(slope, fabsf(rel0 + float(cc + 3)), t3);
+            }
+            e0 *= 1.f - t0 * t0;
+            e1 *= 1.f - t1 * t1;
+            e2 *= 1.f - t2 * t2;
+            e3 *= 1.f - t3 * t3;
+          }
+          dk_[cc / 2] = Elt<T>::pack(e0, e1);
+          dk_[cc / 2 + 1] = Elt<T>::pack(e2, e3);
+        }
+      }
+      tmem_st_x32(t_ds, dk_);
+      {
+        // shared copy for dQ = dS K: panel hf (64 queries = 128 B per key row), 16-byte chunks XOR-swizzled
+        uint8_t* dst = smem_gen + Cfg::kSDS + hf * Cfg::kPanelBytes + r * 128;
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+          *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) =
+              make_uint4(dk_[4 * x], dk_[4 * x + 1], dk_[4 * x + 2], dk_[4 * x + 3]);
+      }
+      tmem_wait_st();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_DSF));
+    }
+    // ---------------------------------------------------------------- epilogue: dK (x scale), dV
+    if (n_iter > 0) {
+      mbar_wait(bar(B_DKV), 0, 710);
+      tc_fence_after();
+    }
+    const int bk = p.cu_seqlens_k ? 0 : bidb;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t t_src = (which == 0 ? tDV : tDK) + lane_sel;
+      const float mul = which == 0 ? 1.0f : p.scale;
+      T* base = reinterpret_cast<T*>(which == 0 ? p.dv : p.dk) +
+                int64_t(bk) * (which == 0 ? p.dv_batch_stride : p.dk_batch_stride) +
+                int64_t(k_off + j) * (which == 0 ? p.dv_row_stride : p.dk_row_stride) +
+                int64_t(hk) * (which == 0 ? p.dv_head_stride : p.dk_head_stride);
+      constexpr int kHalf = kD / 2;  // columns handled by each query-half warp in the epilogue
+#pragma unroll
+      for (int cc = 0; cc < kHalf; cc += 32) {
+        uint32_t o[32];
+        if (n_iter > 0) {
+          tmem_ld_x32(t_src + hf * kHalf + cc, o);
+          tmem_wait_ld();
+        }
+        if (key_valid) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            const int col = hf * kHalf + cc + c;
+            if (col < p.d) {
+              uint4 v4 = make_uint4(0, 0, 0, 0);
+              if (n_iter > 0) {
+                v4.x = Elt<T>::pack(__uint_as_float(o[c]) * mul, __uint_as_float(o[c + 1]) * mul);
+                v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * mul, __uint_as_float(o[c + 3]) * mul);
+                v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * mul, __uint_as_float(o[c + 5]) * mul);
+                v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * mul, __uint_as_float(o[c + 7]) * mul);
+              }
+              *reinterpret_cast<uint4*>(base + col) = v4;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fa
