@@ -99,8 +99,8 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if not os.path.exists(path) or (os.environ.get("FA_B200_REBUILD") == "1"):
+    path = os.environ.get("FA_B200_LIB") or _build.LIB  # FA_B200_LIB: experiment variant built by build.build(out=...)
+    if path == _build.LIB and (not os.path.exists(path) or os.environ.get("FA_B200_REBUILD") == "1"):
         _build.build(force=True)
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():

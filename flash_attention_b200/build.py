@@ -26,20 +26,25 @@ def needs_build():
     return not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest_source_mtime()
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile the library.  `out`/`extra_flags` build an experiment variant next to the default .so
+    (selected at load time with FA_B200_LIB=<path>)."""
+    out = out or LIB
+    if out == LIB and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if os.environ.get("FA_B200_SPIN_GUARD") == "1":
+        extra_flags = tuple(extra_flags) + ("-DFA_SPIN_GUARD=1",)
+    cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(out + ".build.log" if out != LIB else os.path.join(HERE, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if verbose:
         print(log)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + log[-4000:])
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -214,10 +214,10 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 384;
 
   if (warp >= 12) {
-    reg_dealloc<40>();
+    reg_dealloc<96>();
     // ================================================================ TMA producer
     if (warp == 13) {
-      if (lane == 0) {
+      if (elect_one()) {
         const int bk = p.cu_seqlens_k ? 0 : bidb, bq = p.cu_seqlens_q ? 0 : bidb;
         mbar_arrive_expect_tx(bar(B_KV), 2 * Cfg::kTileBytes);
 #pragma unroll
@@ -247,74 +247,78 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
       }
       __syncwarp();
     }
-    // ================================================================ MMA issuer
+    // ================================================================ MMA issuer (one elected thread)
     else if (warp == 12) {
-      if (n_iter > 0) {
+      if (n_iter > 0 && elect_one()) {
         constexpr uint32_t fmt = Elt<T>::kFmt;
         constexpr uint32_t id_s = make_idesc(fmt, fmt, 0, 0, 128, 128);    // S^T, dP^T : K-major A and B
         constexpr uint32_t id_dkv = make_idesc(fmt, fmt, 0, 1, 128, kD);   // dV, dK   : A in TMEM, B MN-major
         constexpr uint32_t id_dq = make_idesc(fmt, fmt, 1, 1, 128, kD);    // dQ       : A and B MN-major
         constexpr uint64_t dk_major = smem_desc_sw128(16, 1024);
         constexpr uint64_t dmn_major = smem_desc_sw128(Cfg::kPanelBytes, 1024);
+        constexpr uint32_t hi_k = uint32_t(dk_major >> 32), hi_mn = uint32_t(dmn_major >> 32);
+        auto lo_k = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | uint32_t(dk_major); };
+        auto lo_mn = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | uint32_t(dmn_major); };
+        auto mk = [](uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; };
         auto mma_kmajor = [&](uint32_t d_t, uint32_t a0, uint32_t b0, uint32_t idesc) {
+          const uint32_t la = lo_k(a0), lb = lo_k(b0);
 #pragma unroll
           for (int kk = 0; kk < kD / 16; ++kk) {
-            const uint32_t off = (kk / 4) * Cfg::kPanelBytes + (kk % 4) * 32;
-            mma_ss<false>(d_t, smem_desc_at(dk_major, a0 + off), smem_desc_at(dk_major, b0 + off), idesc, kk > 0);
+            const uint32_t off = ((kk / 4) * Cfg::kPanelBytes + (kk % 4) * 32) >> 4;
+            mma_ss<false>(d_t, mk(hi_k, la + off), mk(hi_k, lb + off), idesc, kk > 0);
           }
         };
         auto mma_ts_mn = [&](uint32_t d_t, uint32_t a_t, uint32_t b0, bool acc) {
+          const uint32_t lb = lo_mn(b0);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            mma_ts<false>(d_t, a_t + kk * 8, smem_desc_at(dmn_major, b0 + kk * 2048), id_dkv, (acc || kk > 0) ? 1u : 0u);
+            mma_ts<false>(d_t, a_t + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), id_dkv, (acc || kk > 0) ? 1u : 0u);
         };
+        const uint32_t lo_ds = lo_mn(sDS), lo_kmn = lo_mn(sK);
         mbar_wait(bar(B_KV), 0, 500);
         mbar_wait(bar(B_QF0), 0, 501);
         tc_fence_after();
-        if (lane == 0) { mma_kmajor(tS, sK, sQ, id_s); mma_commit(bar(B_SF)); }
+        mma_kmajor(tS, sK, sQ, id_s);
+        mma_commit(bar(B_SF));
         mbar_wait(bar(B_DOF), 0, 502);
         tc_fence_after();
-        if (lane == 0) { mma_kmajor(tDP, sV, sDO, id_s); mma_commit(bar(B_DPF)); }
-        __syncwarp();
+        mma_kmajor(tDP, sV, sDO, id_s);
+        mma_commit(bar(B_DPF));
         for (int it = 0; it < n_iter; ++it) {
           const int st = it & 1;
           const uint32_t ph = it & 1;
           mbar_wait(bar(B_PF), ph, 510);
           tc_fence_after();
-          if (lane == 0) {
-            mma_ts_mn(tDV, tS, sDO, it > 0);
-            mma_commit(bar(B_DOE));
-          }
+          mma_ts_mn(tDV, tS, sDO, it > 0);
+          mma_commit(bar(B_DOE));
           mbar_wait(bar(B_DSF), ph, 511);
           tc_fence_after();
-          if (lane == 0) {
-            mma_ts_mn(tDK, tS + 64, sQ + st * Cfg::kTileBytes, it > 0);
-            mma_commit(bar(B_QE0 + st));
+          mma_ts_mn(tDK, tS + 64, sQ + st * Cfg::kTileBytes, it > 0);
+          mma_commit(bar(B_QE0 + st));
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              mma_ss<false>(tDP, smem_desc_at(dmn_major, sDS + kk * 2048), smem_desc_at(dmn_major, sK + kk * 2048), id_dq,
-                            kk > 0);
-            mma_commit(bar(B_DQF));
-          }
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ss<false>(tDP, mk(hi_mn, lo_ds + kk * (2048 >> 4)), mk(hi_mn, lo_kmn + kk * (2048 >> 4)), id_dq, kk > 0);
+          mma_commit(bar(B_DQF));
           if (it + 1 < n_iter) {
             const int st1 = st ^ 1;
             mbar_wait(bar(B_QF0 + st1), ((it + 1) >> 1) & 1, 512);
             tc_fence_after();
-            if (lane == 0) { mma_kmajor(tS, sK, sQ + st1 * Cfg::kTileBytes, id_s); mma_commit(bar(B_SF)); }
+            mma_kmajor(tS, sK, sQ + st1 * Cfg::kTileBytes, id_s);
+            mma_commit(bar(B_SF));
             mbar_wait(bar(B_DQE), ph, 513);           // dQ_it drained out of TMEM [128,256)
             mbar_wait(bar(B_DOF), (it + 1) & 1, 514);
             tc_fence_after();
-            if (lane == 0) { mma_kmajor(tDP, sV, sDO, id_s); mma_commit(bar(B_DPF)); }
+            mma_kmajor(tDP, sV, sDO, id_s);
+            mma_commit(bar(B_DPF));
           }
-          __syncwarp();
         }
-        if (lane == 0) mma_commit(bar(B_DKV));
+        mma_commit(bar(B_DKV));
       }
       __syncwarp();
     }
   } else if (warp >= 8) {
     // ================================================================ dQ drain: TMEM -> smem -> TMA reduce-add
-    reg_alloc<152>();
+    reg_dealloc<96>();
     const int wq = warp & 3;
     const int r = wq * 32 + lane;  // query row within the block
     const uint32_t t_dq = tDP + (uint32_t(wq * 32) << 16);
@@ -325,30 +329,34 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
       const int m = m_min + it % n_m;
       mbar_wait(bar(B_DQF), it & 1, 600);
       tc_fence_after();
-      uint32_t v[kD];
 #pragma unroll
-      for (int cc = 0; cc < kD; cc += 32) tmem_ld_x32(t_dq + cc, v + cc);
-      tmem_wait_ld();
-      // everything is in registers: hand TMEM [128,256) back to the MMA warp (next dP^T)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_DQE));
+      for (int half = 0; half < kD / 64; ++half) {
+        uint32_t v[64];
+        tmem_ld_x32(t_dq + half * 64, v);
+        tmem_ld_x32(t_dq + half * 64 + 32, v + 32);
+        tmem_wait_ld();
+        if (half == kD / 64 - 1) {  // all of dQ is out of TMEM [128,256): hand it back to the MMA warp (next dP^T)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_DQE));
+        }
 #pragma unroll
-      for (int c = 0; c < kD / 32; ++c, ++nbuf) {
-        const int buf = nbuf & 1;
-        // the TMA reduce that last read this staging buffer must have finished reading it
-        if (leader && nbuf >= 2) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        uint8_t* dst = smem_gen + Cfg::kSDQ + buf * Cfg::kPanelBytes + r * 128;
+        for (int c = 0; c < 2; ++c, ++nbuf) {
+          const int buf = nbuf & 1;
+          // the TMA reduce that last read this staging buffer must have finished reading it
+          if (leader && nbuf >= 2) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint8_t* dst = smem_gen + Cfg::kSDQ + buf * Cfg::kPanelBytes + r * 128;
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-          *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) =
-              make_uint4(v[c * 32 + 4 * x], v[c * 32 + 4 * x + 1], v[c * 32 + 4 * x + 2], v[c * 32 + 4 * x + 3]);
-        fence_proxy_async();
-        named_bar_sync(2, 128);
-        if (leader) {
-          tma_reduce_add_4d(&p.tm_dq, sDQ + buf * Cfg::kPanelBytes, c * 32, m * 128, hq, bidb);
-          tma_store_commit();
+          for (int x = 0; x < 8; ++x)
+            *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) =
+                make_uint4(v[c * 32 + 4 * x], v[c * 32 + 4 * x + 1], v[c * 32 + 4 * x + 2], v[c * 32 + 4 * x + 3]);
+          fence_proxy_async();
+          named_bar_sync(2, 128);
+          if (leader) {
+            tma_reduce_add_4d(&p.tm_dq, sDQ + buf * Cfg::kPanelBytes, half * 64 + c * 32, m * 128, hq, bidb);
+            tma_store_commit();
+          }
         }
       }
     }

@@ -71,7 +71,7 @@ struct FwdCfg {
   static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
   static constexpr int kSmemQ = 2 * kTileBytes;
   static constexpr int kSmemKV = kStages * kTileBytes;
-  static constexpr int kNumBars = 2 + 2 * kStages + 6;
+  static constexpr int kNumBars = 2 + 2 * kStages + 9;
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
 };
 
@@ -88,12 +88,17 @@ template <> struct Elt<__half> {
 
 __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+#ifndef FA_FWD_POLY_PAIRS
+#define FA_FWD_POLY_PAIRS 2
+#endif
+
 template <typename T, int kD>
 __global__ void __launch_bounds__(FwdCfg<kD>::kThreads, 1)
 fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   using Cfg = FwdCfg<kD>;
   constexpr int S = Cfg::kStages;
   constexpr float kNegInf = -INFINITY;
+  constexpr int kPolyPairs = FA_FWD_POLY_PAIRS;  // of every 4 element pairs, how many use the FMA-pipe exp2
 
   // ------------------------------------------------------------------ work item
   const int num_m_blocks = gridDim.x;
@@ -137,6 +142,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
     }
   }
   const int nblocks = n_max > n_min ? n_max - n_min : 0;
+  // the first streamed block is the ragged last block of the sequence
+  const bool v_tail = (n_max == nblk_total) && (sk_b & 127);
 
   // ------------------------------------------------------------------ shared memory carve-up
   extern __shared__ uint8_t smem_raw[];
@@ -149,7 +156,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   auto bar_kv_empty = [&](int s) { return sBar + 8u * (2 + S + s); };
   auto bar_s_full = [&](int i) { return sBar + 8u * (2 + 2 * S + i); };
   auto bar_p_full = [&](int i) { return sBar + 8u * (4 + 2 * S + i); };
-  auto bar_o_full = [&](int i) { return sBar + 8u * (6 + 2 * S + i); };
+  // bar_p_full(i): keys [0,64) of P_i are in TMEM; bar_p_full(i) + 16: keys [64,128)
+  auto bar_o_full = [&](int i) { return sBar + 8u * (8 + 2 * S + i); };
+  const uint32_t bar_v_clean = sBar + 8u * (10 + 2 * S);
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSmemQ + Cfg::kSmemKV + 8 * Cfg::kNumBars);
@@ -168,12 +177,14 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         mbar_init(bar_q_full(i), 1);
         mbar_init(bar_s_full(i), 1);
         mbar_init(bar_p_full(i), 4);  // one arrive per softmax warp
+        mbar_init(bar_p_full(i) + 16, 4);
         mbar_init(bar_o_full(i), 1);
       }
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_kv_full(s), 1);
         mbar_init(bar_kv_empty(s), 1);
       }
+      mbar_init(bar_v_clean, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -187,10 +198,10 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
 
   // register re-distribution (per warpgroup): softmax rows live in registers, the MMA/TMA warps need few
   if (warp >= 8) {
-  reg_dealloc<56>();
+  reg_dealloc<80>();
   // ================================================================== TMA producer
   if (warp == 9) {
-    if (lane == 0 && nblocks > 0) {
+    if (nblocks > 0 && elect_one()) {
       const int bq = p.cu_seqlens_q ? 0 : bidb;
       for (int i = 0; i < ntiles; ++i) {
         mbar_arrive_expect_tx(bar_q_full(i), Cfg::kTileBytes);
@@ -225,33 +236,36 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
     }
     __syncwarp();
   }
-  // ================================================================== MMA issuer
+  // ================================================================== MMA issuer (one elected thread)
   else if (warp == 8) {
-    if (nblocks > 0) {
+    if (nblocks > 0 && elect_one()) {
       constexpr uint32_t fmt = Elt<T>::kFmt;
       constexpr uint32_t idesc_qk = make_idesc(fmt, fmt, 0, 0, 128, 128);
       constexpr uint32_t idesc_pv = make_idesc(fmt, fmt, 0, 1, 128, kD);
       constexpr uint64_t desc_k_major = smem_desc_sw128(16, 1024);
       constexpr uint64_t desc_mn_major = smem_desc_sw128(Cfg::kPanelBytes, 1024);
+      constexpr uint32_t hi_k = uint32_t(desc_k_major >> 32), hi_mn = uint32_t(desc_mn_major >> 32);
+      constexpr uint32_t lo_mn = uint32_t(desc_mn_major);  // carries the LBO field
+      auto lo_of = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
+      auto mk = [](uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; };
       const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
 
       auto issue_qk = [&](int i, int slot_k) {
-        const uint32_t a0 = sQ + i * Cfg::kTileBytes;
-        const uint32_t b0 = sKV + slot_k * Cfg::kTileBytes;
+        const uint32_t la = lo_of(sQ + i * Cfg::kTileBytes) | uint32_t(desc_k_major);
+        const uint32_t lb = lo_of(sKV + slot_k * Cfg::kTileBytes) | uint32_t(desc_k_major);
 #pragma unroll
         for (int kk = 0; kk < kD / 16; ++kk) {
-          const uint32_t off = (kk / 4) * Cfg::kPanelBytes + (kk % 4) * 32;
-          mma_ss<false>(tS[i], smem_desc_at(desc_k_major, a0 + off), smem_desc_at(desc_k_major, b0 + off), idesc_qk,
-                        kk > 0);
+          const uint32_t off = ((kk / 4) * Cfg::kPanelBytes + (kk % 4) * 32) >> 4;
+          mma_ss<false>(tS[i], mk(hi_k, la + off), mk(hi_k, lb + off), idesc_qk, kk > 0);
         }
       };
-      auto issue_pv = [&](int i, int slot_v, bool acc) {
-        const uint32_t b0 = sKV + slot_v * Cfg::kTileBytes;
+      auto issue_pv = [&](int i, int slot_v, bool acc, int half) {
+        const uint32_t lb = lo_of(sKV + slot_v * Cfg::kTileBytes) | lo_mn;
 #pragma unroll
-        for (int kk = 0; kk < 128 / 16; ++kk) {
-          mma_ts<false>(tO[i], tS[i] + kk * 8, smem_desc_at(desc_mn_major, b0 + kk * 2048), idesc_pv,
-                        (acc || kk > 0) ? 1u : 0u);
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int kk = half * 4 + k4;
+          mma_ts<false>(tO[i], tS[i] + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), idesc_pv, (acc || kk > 0) ? 1u : 0u);
         }
       };
 
@@ -259,62 +273,63 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       // prologue: S_i = Q_i K_0^T
       mbar_wait(bar_kv_full(0), 0, 210);
       tc_fence_after();
-      if (lane == 0) {
-        for (int i = 0; i < ntiles; ++i) {
-          issue_qk(i, 0);
-          mma_commit(bar_s_full(i));
-        }
-        mma_commit(bar_kv_empty(0));
+      for (int i = 0; i < ntiles; ++i) {
+        issue_qk(i, 0);
+        mma_commit(bar_s_full(i));
       }
-      __syncwarp();
+      mma_commit(bar_kv_empty(0));
       for (int it = 0; it < nblocks; ++it) {
         const int ring_v = 2 * it + 1, ring_k = 2 * it + 2;
         const int sv = ring_v % S, sk_ = ring_k % S;
         const uint32_t phv = (ring_v / S) & 1, phk = (ring_k / S) & 1;
         const bool more = it + 1 < nblocks;
-        mbar_wait(bar_kv_full(sv), phv, 220);
-        if (it == 0 && n_max == nblk_total && (sk_b & 127)) {
-          // Rows of the last V block beyond seqlen_k may hold garbage (kv-cache tail, next sequence):
-          // P is exactly 0 there but 0 * NaN would poison O, so clear them
-          // (reference: Clear_OOB_MN on the V load, flash_fwd_kernel.h:254-262).
-          const int valid = sk_b - (nblk_total - 1) * 128;
-          const int nvec = (128 - valid) * 8;
-          for (int pn = 0; pn < Cfg::kPanels; ++pn) {
-            uint4* base = reinterpret_cast<uint4*>(smem_gen + Cfg::kSmemQ + sv * Cfg::kTileBytes +
-                                                   pn * Cfg::kPanelBytes + valid * 128);
-            for (int x = lane; x < nvec; x += 32) base[x] = make_uint4(0, 0, 0, 0);
-          }
-          fence_proxy_async();
-          __syncwarp();
-        }
+        if (it == 0 && v_tail) mbar_wait(bar_v_clean, 0, 221);  // warp 10 has zeroed the rows beyond seqlen_k
+        else mbar_wait(bar_kv_full(sv), phv, 220);
         for (int i = 0; i < ntiles; ++i) {
           mbar_wait(bar_p_full(i), it & 1, 230 + i);
           tc_fence_after();
-          if (lane == 0) {
-            issue_pv(i, sv, it > 0);
-            mma_commit(bar_o_full(i));
-            if (i == ntiles - 1) mma_commit(bar_kv_empty(sv));
-          }
+          issue_pv(i, sv, it > 0, 0);
+          mbar_wait(bar_p_full(i) + 16, it & 1, 232 + i);
+          tc_fence_after();
+          issue_pv(i, sv, it > 0, 1);
+          mma_commit(bar_o_full(i));
+          if (i == ntiles - 1) mma_commit(bar_kv_empty(sv));
           if (more) {
             if (i == 0) {
               mbar_wait(bar_kv_full(sk_), phk, 240);
               tc_fence_after();
             }
-            if (lane == 0) {
-              issue_qk(i, sk_);
-              mma_commit(bar_s_full(i));
-              if (i == ntiles - 1) mma_commit(bar_kv_empty(sk_));
-            }
+            issue_qk(i, sk_);
+            mma_commit(bar_s_full(i));
+            if (i == ntiles - 1) mma_commit(bar_kv_empty(sk_));
           }
-          __syncwarp();
         }
       }
     }
     __syncwarp();
   }
+  // ================================================================== V-tail cleaner (otherwise idle warp)
+  else if (warp == 10) {
+    if (nblocks > 0 && v_tail) {
+      // Rows of the last V block beyond seqlen_k may hold garbage (kv-cache tail, next sequence): P is
+      // exactly 0 there but 0 * NaN would poison O, so clear them before the first PV
+      // (reference: Clear_OOB_MN on the V load, flash_fwd_kernel.h:254-262).
+      mbar_wait(bar_kv_full(1), 0, 250);
+      const int valid = sk_b - (nblk_total - 1) * 128;
+      const int nvec = (128 - valid) * 8;
+      for (int pn = 0; pn < Cfg::kPanels; ++pn) {
+        uint4* base = reinterpret_cast<uint4*>(smem_gen + Cfg::kSmemQ + 1 * Cfg::kTileBytes + pn * Cfg::kPanelBytes +
+                                               valid * 128);
+        for (int x = lane; x < nvec; x += 32) base[x] = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_v_clean);
+    }
+  }
   } else {
   // ================================================================== softmax warpgroups
-    reg_alloc<224>();
+    reg_alloc<216>();
     const int tile = warp >> 2;
     if (tile < ntiles) {
       const int wq = warp & 3;
@@ -344,39 +359,74 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         mbar_wait(bar_s_full(tile), it & 1, 300 + tile);
         tc_fence_after();
         uint32_t su[128];
-        tmem_ld_x32(tS + 0, su);
-        tmem_ld_x32(tS + 32, su + 32);
-        tmem_ld_x32(tS + 64, su + 64);
-        tmem_ld_x32(tS + 96, su + 96);
-        tmem_wait_ld();
         float* s = reinterpret_cast<float*>(su);
-        if (p.debug_s && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile == 0 && it == 0) {
-#pragma unroll
-          for (int c = 0; c < 128; ++c) p.debug_s[(wq * 32 + lane) * 128 + c] = s[c];
-        }
-        if (p.softcap_pre != 0.f) {
-#pragma unroll
-          for (int c = 0; c < 128; ++c) s[c] = tanh_approx(s[c] * p.softcap_pre);
-        }
-        if (p.alibi_slopes) {  // bias = -slope * |i + sk - sq - j|  (mask.h:148-165)
-          const float rel0 = float(qpos + shift - col0);
-#pragma unroll
-          for (int c = 0; c < 128; ++c) s[c] = fmaf(-slope, fabsf(rel0 - float(c)), s[c]);
-        }
-        // masking: only blocks that cross a limit of some row of this tile (warp-uniform test)
+        // which blocks need the slow path (score mods / masks)?  warp-uniform
         bool need_mask = col0 + 128 > sk_b;
         if (p.has_right) need_mask |= col0 + 128 > t_qlo + 1 + shift + p.wr;
         if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
-        if (need_mask) {
-          const int hi = col_hi - col0, lo = col_lo - col0;
+        const bool slow = need_mask || p.softcap_pre != 0.f || p.alibi_slopes != nullptr ||
+                          (p.debug_s != nullptr && it == 0);
+        float mx;
+        if (!slow) {
+          // fast path: second half of the row streams out of TMEM while the first half is reduced
+          tmem_ld_x32(tS + 0, su);
+          tmem_ld_x32(tS + 32, su + 32);
+          tmem_wait_ld();
+          tmem_ld_x32(tS + 64, su + 64);
+          tmem_ld_x32(tS + 96, su + 96);
+          float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]);
+          float m2 = fmax3(s[6], s[7], s[8]), m3 = fmax3(s[9], s[10], s[11]);
 #pragma unroll
-          for (int c = 0; c < 128; ++c) s[c] = (c >= hi || c < lo) ? kNegInf : s[c];
+          for (int c = 12; c + 7 < 64; c += 8) {
+            m0 = fmax3(m0, s[c], s[c + 1]);
+            m1 = fmax3(m1, s[c + 2], s[c + 3]);
+            m2 = fmax3(m2, s[c + 4], s[c + 5]);
+            m3 = fmax3(m3, s[c + 6], s[c + 7]);
+          }
+          m0 = fmax3(m0, s[60], s[61]);
+          m1 = fmax3(m1, s[62], s[63]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 64; c + 7 < 128; c += 8) {
+            m0 = fmax3(m0, s[c], s[c + 1]);
+            m1 = fmax3(m1, s[c + 2], s[c + 3]);
+            m2 = fmax3(m2, s[c + 4], s[c + 5]);
+            m3 = fmax3(m3, s[c + 6], s[c + 7]);
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+          tmem_ld_x32(tS + 0, su);
+          tmem_ld_x32(tS + 32, su + 32);
+          tmem_ld_x32(tS + 64, su + 64);
+          tmem_ld_x32(tS + 96, su + 96);
+          tmem_wait_ld();
+          if (p.debug_s && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile == 0 && it == 0) {
+#pragma unroll
+            for (int c = 0; c < 128; ++c) p.debug_s[(wq * 32 + lane) * 128 + c] = s[c];
+          }
+          if (p.softcap_pre != 0.f) {
+#pragma unroll
+            for (int c = 0; c < 128; ++c) s[c] = tanh_approx(s[c] * p.softcap_pre);
+          }
+          if (p.alibi_slopes) {  // bias = -slope * |i + sk - sq - j|  (mask.h:148-165)
+            const float rel0 = float(qpos + shift - col0);
+#pragma unroll
+            for (int c = 0; c < 128; ++c) s[c] = fmaf(-slope, fabsf(rel0 - float(c)), s[c]);
+          }
+          if (need_mask) {
+            const int hi = col_hi - col0, lo = col_lo - col0;
+#pragma unroll
+            for (int c = 0; c < 128; ++c) s[c] = (c >= hi || c < lo) ? kNegInf : s[c];
+          }
+          float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]);
+#pragma unroll
+          for (int c = 6; c + 3 < 128; c += 4) {
+            m0 = fmax3(m0, s[c], s[c + 1]);
+            m1 = fmax3(m1, s[c + 2], s[c + 3]);
+          }
+          mx = fmax3(m0, m1, fmaxf(s[126], s[127]));
         }
         // ---- online softmax: row max with a lazily updated reference (exact after normalisation)
-        float mx = fmax3(s[0], s[1], s[2]);
-#pragma unroll
-        for (int c = 3; c + 1 < 128; c += 2) mx = fmax3(mx, s[c], s[c + 1]);
-        mx = fmaxf(mx, s[127]);
         const float m_new = fmaxf(m_ref, mx);
         if (it == 0) {
           m_ref = m_new;
@@ -404,26 +454,42 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           }
         }
         const float neg_ms = (m_ref == kNegInf) ? 0.f : -m_ref * scale_log2;
-        // ---- P = exp2(S*scale_log2 - m*scale_log2), written back over S as packed 16-bit
-        float acc0 = 0.f, acc1 = 0.f;
+        // ---- P = exp2(S*scale_log2 - m*scale_log2), written back over S as packed 16-bit.
+        // Packed FFMA2 for the scaling; kPolyPairs of every 4 pairs take the FMA-pipe polynomial instead
+        // of MUFU.EX2 (the MUFU unit, 16 op/clk/SM, is otherwise as busy as the tensor pipe).
+        const uint64_t sc2 = pack2(scale_log2, scale_log2), ng2 = pack2(neg_ms, neg_ms);
+        uint64_t acc_a = pack2(0.f, 0.f), acc_b = pack2(0.f, 0.f);
 #pragma unroll
         for (int cc = 0; cc < 128; cc += 32) {
           uint32_t pk[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            const float e0 = ex2(fmaf(s[cc + c], scale_log2, neg_ms));
-            const float e1 = ex2(fmaf(s[cc + c + 1], scale_log2, neg_ms));
-            acc0 += e0;
-            acc1 += e1;
+            float x0, x1, e0, e1;
+            unpack2(fma2(pack2(s[cc + c], s[cc + c + 1]), sc2, ng2), x0, x1);
+            if (((c >> 1) & 3) < 4 - kPolyPairs) {
+              e0 = ex2(x0);
+              e1 = ex2(x1);
+            } else {
+              ex2_poly2(x0, x1, e0, e1);
+            }
+            if (c & 2) acc_b = add2(acc_b, pack2(e0, e1));
+            else acc_a = add2(acc_a, pack2(e0, e1));
             pk[c / 2] = Elt<T>::pack(e0, e1);
           }
           tmem_st_x16(tS + cc / 2, pk);
+          if (cc == 32 || cc == 96) {  // half of P is in TMEM: let the first / second half of P V start
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_p_full(tile) + (cc == 96 ? 16u : 0u));
+          }
         }
-        row_sum += acc0 + acc1;
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p_full(tile));
+        {
+          float a0, a1, b0, b1;
+          unpack2(acc_a, a0, a1);
+          unpack2(acc_b, b0, b1);
+          row_sum += (a0 + a1) + (b0 + b1);
+        }
       }
 
       // ---------------------------------------------------------------- epilogue

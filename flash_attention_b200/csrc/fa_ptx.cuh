@@ -9,8 +9,10 @@
 
 #include "fa_tmem_ldst.cuh"
 
+// FA_SPIN_GUARD=1 (build with FA_B200_SPIN_GUARD=1): every mbarrier wait gives up after ~2^24 polls, prints
+// which barrier starved and traps -- bring-up aid; off in the shipped build.
 #ifndef FA_SPIN_GUARD
-#define FA_SPIN_GUARD 1
+#define FA_SPIN_GUARD 0
 #endif
 
 namespace fa {
@@ -213,6 +215,46 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
   return y;
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100: two fp32 lanes per instruction)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for a pair on the FMA pipe (no MUFU): round-to-nearest range reduction x = n + f, f in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5, far below the 16-bit rounding of P), 2^n by
+// adding n to the exponent field.  Inputs must be <= ~120; values below -125 are clamped (result ~ 1e-38, i.e. 0 after 16-bit rounding).
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& r1) {
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it rounds to an integer kept in the low mantissa bits
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t t = add2(x, pack2(kMagic, kMagic));
+  const uint64_t n = add2(t, pack2(-kMagic, -kMagic));
+  const uint64_t f = fma2(n, pack2(-1.0f, -1.0f), x);
+  uint64_t pl = fma2(f, pack2(0.0551716648f, 0.0551716648f), pack2(0.2426111251f, 0.2426111251f));
+  pl = fma2(pl, f, pack2(0.6932609677f, 0.6932609677f));
+  pl = fma2(pl, f, pack2(0.9999280572f, 0.9999280572f));
+  float t0, t1, p0, p1;
+  unpack2(t, t0, t1);
+  unpack2(pl, p0, p1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // {lo, hi} -> packed 16-bit pair (lo in bits [0,16))
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
