@@ -30,7 +30,8 @@ class FwdArgs(C.Structure):
         ("b", _i32), ("seqlen_q", _i32), ("seqlen_k", _i32), ("h", _i32), ("h_k", _i32), ("d", _i32),
         ("total_q", _i32), ("total_k", _i32),
         ("dtype", _i32),
-        ("cu_seqlens_q", _vp), ("cu_seqlens_k", _vp), ("seqused_k", _vp), ("block_table", _vp),
+        ("cu_seqlens_q", _vp), ("cu_seqlens_k", _vp), ("seqused_k", _vp),
+        ("cache_batch_idx", _vp), ("leftpad_k", _vp), ("block_table", _vp),
         ("block_table_batch_stride", _i64),
         ("page_block_size", _i32), ("num_pages", _i32),
         ("alibi_slopes", _vp), ("alibi_slopes_batch_stride", _i64),
@@ -70,6 +71,25 @@ class BwdArgs(C.Structure):
     ]
 
 
+class AppendArgs(C.Structure):
+    """Mirror of `fa_b200_append_args`."""
+
+    _fields_ = [
+        ("kcache", _vp), ("vcache", _vp), ("knew", _vp), ("vnew", _vp), ("q", _vp), ("q_out", _vp),
+        ("kc_batch_stride", _i64), ("kc_row_stride", _i64), ("kc_head_stride", _i64),
+        ("vc_batch_stride", _i64), ("vc_row_stride", _i64), ("vc_head_stride", _i64),
+        ("kn_batch_stride", _i64), ("kn_row_stride", _i64), ("kn_head_stride", _i64),
+        ("vn_batch_stride", _i64), ("vn_row_stride", _i64), ("vn_head_stride", _i64),
+        ("q_batch_stride", _i64), ("q_row_stride", _i64), ("q_head_stride", _i64),
+        ("qo_batch_stride", _i64), ("qo_row_stride", _i64), ("qo_head_stride", _i64),
+        ("cache_seqlens", _vp), ("cache_batch_idx", _vp), ("leftpad_k", _vp),
+        ("block_table", _vp), ("block_table_batch_stride", _i64), ("page_block_size", _i32),
+        ("rotary_cos", _vp), ("rotary_sin", _vp),
+        ("rotary_dim", _i32), ("is_rotary_interleaved", _i32), ("q_pos_per_row", _i32),
+        ("b", _i32), ("seqlen_new", _i32), ("seqlen_q", _i32), ("h", _i32), ("h_k", _i32), ("d", _i32), ("dtype", _i32),
+    ]
+
+
 # every symbol include/fa_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "fa_b200_mha_fwd": (C.c_int, [C.POINTER(FwdArgs), _vp]),
@@ -81,6 +101,8 @@ SYMBOLS = {
     "fa_b200_mha_varlen_bwd": (C.c_int, [C.POINTER(BwdArgs), _vp]),
     "fa_b200_bwd_workspace_bytes": (_sz, [C.POINTER(BwdArgs)]),
     "fa_b200_fwd_combine": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp]),
+    "fa_b200_kvcache_append": (C.c_int, [C.POINTER(AppendArgs), _vp]),
+    "fa_b200_sizeof_append_args": (_sz, []),
     "fa_b200_num_splits_heuristic": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fa_b200_last_error": (C.c_char_p, []),
     "fa_b200_sizeof_fwd_args": (_sz, []),
@@ -107,7 +129,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.fa_b200_sizeof_fwd_args() != C.sizeof(FwdArgs) or lib.fa_b200_sizeof_bwd_args() != C.sizeof(BwdArgs):
+    if (lib.fa_b200_sizeof_fwd_args() != C.sizeof(FwdArgs) or lib.fa_b200_sizeof_bwd_args() != C.sizeof(BwdArgs)
+            or lib.fa_b200_sizeof_append_args() != C.sizeof(AppendArgs)):
         raise RuntimeError(
             "fa_b200 ABI mismatch: ctypes struct size %d/%d vs library %d/%d"
             % (C.sizeof(FwdArgs), C.sizeof(BwdArgs), lib.fa_b200_sizeof_fwd_args(), lib.fa_b200_sizeof_bwd_args())

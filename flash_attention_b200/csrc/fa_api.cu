@@ -14,6 +14,7 @@
 #include "fa_api_common.h"
 #include "fa_combine.cuh"
 #include "fa_fwd_sm100.cuh"
+#include "fa_kvcache.cuh"
 
 namespace fa {
 
@@ -120,10 +121,8 @@ struct FwdPlan {
 };
 
 static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
-  if (a.dtype != FA_B200_FP16 && a.dtype != FA_B200_BF16) {
-    if (a.dtype == FA_B200_FP8_E4M3) return set_error("fp8 e4m3 forward is not built in this revision");
-    return set_error("FlashAttention only support fp16 and bf16 data type");
-  }
+  if (a.dtype != FA_B200_FP16 && a.dtype != FA_B200_BF16 && a.dtype != FA_B200_FP8_E4M3)
+    return set_error("FlashAttention only support fp16, bf16 and fp8 e4m3 (forward) data type");
   if (!a.q || !a.k || !a.v || !a.out || !a.softmax_lse) return set_error("q, k, v, out, softmax_lse must be non-null");
   if (a.b <= 0) return set_error("batch size must be positive");
   if (a.d <= 0 || a.d > 256) return set_error("FlashAttention forward only supports head dimension at most 256");
@@ -133,12 +132,16 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     return set_error("Number of heads in key/value must divide number of heads in query");
   if (a.softcap < 0.f) return set_error("softcap must be non-negative");
   if (mode == kVarlen && (!a.cu_seqlens_q || !a.cu_seqlens_k)) return set_error("cu_seqlens_q and cu_seqlens_k are required");
+  if ((a.cache_batch_idx || a.leftpad_k) && mode != kKvcache) return set_error("cache_batch_idx / leftpad_k are kvcache-only arguments");
+  if (a.block_table && (a.cache_batch_idx || a.leftpad_k))
+    return set_error("We don't support Paged KV and leftpad_k / cache_batch_idx running at the same time yet");
   if (a.block_table) {
     if (a.page_block_size <= 0 || a.page_block_size % 128 != 0)
       return set_error("Paged KV cache block size must be divisible by 128");
     if (a.num_pages <= 0) return set_error("num_pages must be positive for a paged KV cache");
   }
-  pl->kD = a.d <= 64 ? 64 : 128;
+  pl->kD = (a.d <= 64 && a.dtype != FA_B200_FP8_E4M3) ? 64 : 128;  // fp8 rows are always one 128-byte panel
+  if (a.dtype == FA_B200_FP8_E4M3 && a.d % 16 != 0) return set_error("fp8 head_size should be a multiple of 16");
   // window canonicalisation (flash_api.cpp:414-419, set_params_fprop :150-164)
   int wl = a.window_size_left, wr = a.window_size_right;
   int causal = a.is_causal;
@@ -185,7 +188,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
 
 template <typename T, int kD>
 static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
-  using Cfg = FwdCfg<kD>;
+  using Cfg = FwdCfg<kD, EltInfo<T>::kBytes>;
   static bool configured = false;
   auto kern = fa_fwd_kernel<T, kD>;
   if (!configured) {
@@ -207,8 +210,11 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     return set_error("workspace too small for split-KV (query fa_b200_fwd_workspace_bytes)");
   if (a.seqlen_q == 0 || (mode == kVarlen && a.total_q == 0)) return 0;
 
-  const int esz = 2;
-  const CUtensorMapDataType dt = a.dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const bool fp8 = a.dtype == FA_B200_FP8_E4M3;
+  const int esz = fp8 ? 1 : 2;
+  const uint32_t panel = 128 / esz;  // elements per 128-byte swizzle row
+  const CUtensorMapDataType dt = fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                     : (a.dtype == FA_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   const int g = a.h / a.h_k, gp = pl.gp;
   FwdKernelParams kp;
   memset(&kp, 0, sizeof kp);
@@ -221,7 +227,7 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
                        uint64_t(a.q_head_stride) * gp * esz,
                        uint64_t(varlen ? int64_t(a.total_q) * a.q_row_stride : a.q_batch_stride) * esz};
     if (dims[4] == 1) str[3] = dims[2] * str[1];  // any valid value
-    uint32_t box[5] = {64, uint32_t(gp), uint32_t(128 / gp), 1, 1};
+    uint32_t box[5] = {panel, uint32_t(gp), uint32_t(128 / gp), 1, 1};
     if (int rc = make_tmap(&kp.tm_q, dt, 5, a.q, dims, str, box)) return rc;
   }
   for (int which = 0; which < 2; ++which) {
@@ -236,7 +242,7 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     uint64_t dims[4] = {uint64_t(a.d), rows, uint64_t(a.h_k), nb};
     uint64_t str[3] = {uint64_t(rs) * esz, uint64_t(hs) * esz, uint64_t(bs) * esz};
     if (nb == 1) str[2] = rows * str[0];
-    uint32_t box[4] = {64, 128, 1, 1};
+    uint32_t box[4] = {panel, 128, 1, 1};
     if (int rc = make_tmap(which == 0 ? &kp.tm_k : &kp.tm_v, dt, 4, base, dims, str, box)) return rc;
   }
   kp.o = a.out;
@@ -247,11 +253,15 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   kp.cu_seqlens_q = a.cu_seqlens_q;
   kp.cu_seqlens_k = a.cu_seqlens_k;
   kp.seqused_k = a.seqused_k;
+  kp.cache_batch_idx = a.cache_batch_idx;
+  kp.leftpad_k = a.leftpad_k;
   kp.block_table = a.block_table;
   kp.block_table_batch_stride = a.block_table_batch_stride;
   kp.alibi_slopes = a.alibi_slopes;
   kp.alibi_batch_stride = a.alibi_slopes_batch_stride;
   kp.debug_s = a.debug_s;
+  kp.q_descale = a.q_descale; kp.k_descale = a.k_descale; kp.v_descale = a.v_descale;
+  kp.q_descale_bs = a.q_descale_batch_stride; kp.k_descale_bs = a.k_descale_batch_stride; kp.v_descale_bs = a.v_descale_batch_stride;
   kp.b = a.b; kp.h = a.h; kp.h_k = a.h_k; kp.sq = a.seqlen_q; kp.sk = a.seqlen_k; kp.d = a.d;
   kp.g = g; kp.gp = gp; kp.total_q = a.total_q;
   kp.page_size = a.block_table ? a.page_block_size : 0;
@@ -273,7 +283,9 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   }
   dim3 grid(pl.num_m_blocks, a.h / gp, a.b * pl.num_splits);
   int rc;
-  if (a.dtype == FA_B200_BF16) {
+  if (fp8) {
+    rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream);
+  } else if (a.dtype == FA_B200_BF16) {
     rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream)
                      : launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream);
   } else {
@@ -294,8 +306,8 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     cp.sq = a.seqlen_q;
     cp.obs = a.o_batch_stride; cp.ors = a.o_row_stride; cp.ohs = a.o_head_stride;
     const unsigned blocks = unsigned((cp.rows + 7) / 8);
-    if (a.dtype == FA_B200_BF16) fa_combine_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(cp);
-    else fa_combine_kernel<__half><<<blocks, 256, 0, stream>>>(cp);
+    if (a.dtype == FA_B200_FP16) fa_combine_kernel<__half><<<blocks, 256, 0, stream>>>(cp);
+    else fa_combine_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(cp);
     g_launch_count++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(std::string("fa_combine_kernel launch: ") + cudaGetErrorString(e));
@@ -365,6 +377,44 @@ int fa_b200_fwd_combine(const float* o_partial, const float* lse_partial, void* 
 int fa_b200_num_splits_heuristic(int batch_nheads_mblocks, int num_sms_, int num_n_blocks, int max_splits) {
   return splits_heuristic(batch_nheads_mblocks, num_sms_, num_n_blocks, max_splits);
 }
+
+int fa_b200_kvcache_append(const fa_b200_append_args* a, fa_b200_stream_t stream) {
+  if (!a) return set_error("null args");
+  if (a->dtype != FA_B200_FP16 && a->dtype != FA_B200_BF16) return set_error("kvcache append supports fp16 and bf16");
+  if (!a->cache_seqlens) return set_error("If key is supplied, seqlens_k must also be passed in");
+  if (a->knew && (!a->vnew || !a->kcache || !a->vcache)) return set_error("If key is supplied, value must also be passed in");
+  if (a->rotary_cos) {
+    if (!a->rotary_sin) return set_error("rotary_sin is required with rotary_cos");
+    if (a->rotary_dim <= 0 || a->rotary_dim > a->d || a->rotary_dim % 16 != 0)
+      return set_error("Only rotary dimensions divisible by 16 are currently supported");
+  }
+  if (a->block_table && (a->page_block_size <= 0)) return set_error("page_block_size must be positive");
+  AppendParams p;
+  p.kcache = a->kcache; p.vcache = a->vcache; p.knew = a->knew; p.vnew = a->vnew; p.q = a->q; p.q_out = a->q_out;
+  p.kc_bs = a->kc_batch_stride; p.kc_rs = a->kc_row_stride; p.kc_hs = a->kc_head_stride;
+  p.vc_bs = a->vc_batch_stride; p.vc_rs = a->vc_row_stride; p.vc_hs = a->vc_head_stride;
+  p.kn_bs = a->kn_batch_stride; p.kn_rs = a->kn_row_stride; p.kn_hs = a->kn_head_stride;
+  p.vn_bs = a->vn_batch_stride; p.vn_rs = a->vn_row_stride; p.vn_hs = a->vn_head_stride;
+  p.q_bs = a->q_batch_stride; p.q_rs = a->q_row_stride; p.q_hs = a->q_head_stride;
+  p.qo_bs = a->qo_batch_stride; p.qo_rs = a->qo_row_stride; p.qo_hs = a->qo_head_stride;
+  p.cache_seqlens = a->cache_seqlens; p.cache_batch_idx = a->cache_batch_idx; p.leftpad_k = a->leftpad_k;
+  p.block_table = a->block_table; p.bt_bs = a->block_table_batch_stride; p.page_size = a->page_block_size;
+  p.rot_cos = a->rotary_cos; p.rot_sin = a->rotary_sin; p.rotary_dim = a->rotary_dim;
+  p.interleaved = a->is_rotary_interleaved; p.q_pos_per_row = a->q_pos_per_row;
+  p.b = a->b; p.s_new = a->knew ? a->seqlen_new : 0; p.sq = (a->rotary_cos && a->q_out) ? a->seqlen_q : 0;
+  p.h = a->h; p.h_k = a->h_k; p.d = a->d;
+  const int rows = p.s_new > p.sq ? p.s_new : p.sq, heads = a->h > a->h_k ? a->h : a->h_k;
+  if (rows == 0 || a->b == 0) return 0;
+  dim3 grid(rows, heads, a->b);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == FA_B200_BF16) fa_kv_append_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
+  else fa_kv_append_kernel<__half><<<grid, 128, 0, s>>>(p);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_kv_append_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+size_t fa_b200_sizeof_append_args(void) { return sizeof(fa_b200_append_args); }
 
 const char* fa_b200_last_error(void) { return g_last_error.c_str(); }
 size_t fa_b200_sizeof_fwd_args(void) { return sizeof(fa_b200_fwd_args); }

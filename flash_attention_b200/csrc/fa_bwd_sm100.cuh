@@ -54,6 +54,9 @@ struct BwdKernelParams {
 template <int kD>
 struct BwdCfg {
   static constexpr int kThreads = 512;
+  // setmaxnreg split over the 4 warpgroups (pool = 512 threads x 128 regs): compute, compute, drain, MMA/TMA
+  static constexpr int kRegsCompute = 160, kRegsDrain = 96, kRegsOther = 96;
+  static_assert(2 * kRegsCompute + kRegsDrain + kRegsOther <= 4 * 128, "setmaxnreg split exceeds the CTA register pool");
   static constexpr int kPanels = kD / 64;
   static constexpr int kPanelBytes = 128 * 128;
   static constexpr int kTileBytes = kPanels * kPanelBytes;   // one 128-row 16-bit tile
@@ -214,7 +217,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 384;
 
   if (warp >= 12) {
-    reg_dealloc<96>();
+    reg_dealloc<Cfg::kRegsOther>();
     // ================================================================ TMA producer
     if (warp == 13) {
       if (elect_one()) {
@@ -318,7 +321,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
     }
   } else if (warp >= 8) {
     // ================================================================ dQ drain: TMEM -> smem -> TMA reduce-add
-    reg_dealloc<96>();
+    reg_dealloc<Cfg::kRegsDrain>();
     const int wq = warp & 3;
     const int r = wq * 32 + lane;  // query row within the block
     const uint32_t t_dq = tDP + (uint32_t(wq * 32) << 16);
@@ -363,7 +366,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
     if (leader) tma_store_wait<0>();
   } else {
     // ================================================================ compute warps
-    reg_alloc<160>();
+    reg_alloc<Cfg::kRegsCompute>();
     const int wq = warp & 3, hf = warp >> 2;          // key-row quadrant, query half
     const int r = wq * 32 + lane;                       // key row within the block
     const int j = key0 + r;                             // key index in the sequence

@@ -37,6 +37,8 @@ struct FwdKernelParams {
   const int* cu_seqlens_q;
   const int* cu_seqlens_k;
   const int* seqused_k;
+  const int* cache_batch_idx;  // kvcache: batch b reads cache row cache_batch_idx[b]
+  const int* leftpad_k;        // kvcache: first valid key row of batch b
   const int* block_table;
   int64_t block_table_batch_stride;
   const float* alibi_slopes;
@@ -60,13 +62,19 @@ struct FwdKernelParams {
   float softcap_pre;        // softmax_scale / softcap, 0 = off
 };
 
-template <int kD>
+template <int kD, int kBytes = 2>
 struct FwdCfg {
   static constexpr int kBlockM = 128;
   static constexpr int kBlockN = 128;
   static constexpr int kStages = 5;
   static constexpr int kThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle}
-  static constexpr int kPanels = kD / 64;                 // 64-element (128 B) swizzle panels per row
+  // setmaxnreg split: the CTA's register pool is kThreads * 168 (launch bounds 384 x 1 -> 168 regs/thread);
+  // 2 softmax warpgroups + 1 MMA/TMA warpgroup must not ask for more than that or setmaxnreg.inc blocks forever.
+  static constexpr int kRegsSoftmax = 216;
+  static constexpr int kRegsOther = 72;
+  static_assert(2 * kRegsSoftmax + kRegsOther <= 3 * 168, "setmaxnreg split exceeds the CTA register pool");
+  static constexpr int kPanels = kD * kBytes / 128;        // 128-byte swizzle panels per row (64 x 16-bit or 128 x 8-bit)
+  static constexpr int kPanelElems = 128 / kBytes;
   static constexpr int kPanelBytes = 128 * 128;           // 128 rows x 128 B
   static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
   static constexpr int kSmemQ = 2 * kTileBytes;
@@ -85,6 +93,15 @@ template <> struct Elt<__half> {
   static constexpr uint32_t kFmt = 0;
   static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return pack_f16(lo, hi); }
 };
+// FP8 e4m3 inputs (forward only): kind::f8f6f4 MMA, P quantised to e4m3 after a 2^8 up-scale, bf16 output
+// (spec: hopper/flash_api.cpp mha_fwd descales; flash_attn/cute/flash_fwd_sm100.py:2003-2020,2179-2201)
+struct fp8_e4m3 {};
+template <> struct Elt<fp8_e4m3> {
+  static constexpr uint32_t kFmt = 0;  // E4M3 in the f8f6f4 instruction descriptor
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return pack_bf16(lo, hi); }  // output = bf16
+};
+template <typename T> struct EltInfo { static constexpr int kBytes = 2; static constexpr bool kFp8 = false; using Out = T; };
+template <> struct EltInfo<fp8_e4m3> { static constexpr int kBytes = 1; static constexpr bool kFp8 = true; using Out = __nv_bfloat16; };
 
 __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -95,7 +112,10 @@ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; 
 template <typename T, int kD>
 __global__ void __launch_bounds__(FwdCfg<kD>::kThreads, 1)
 fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
-  using Cfg = FwdCfg<kD>;
+  constexpr int kBytes = EltInfo<T>::kBytes;
+  constexpr bool kFp8 = EltInfo<T>::kFp8;
+  using OutT = typename EltInfo<T>::Out;
+  using Cfg = FwdCfg<kD, kBytes>;
   constexpr int S = Cfg::kStages;
   constexpr float kNegInf = -INFINITY;
   constexpr int kPolyPairs = FA_FWD_POLY_PAIRS;  // of every 4 element pairs, how many use the FMA-pipe exp2
@@ -111,6 +131,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
   if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
   if (p.seqused_k) sk_b = p.seqused_k[bidb];
+  if (p.leftpad_k) { k_off = p.leftpad_k[bidb]; sk_b -= k_off; }  // seqlen_k = seqused_k - leftpad_k (block_info.h:12-45)
   const int rows_total = sq_b * p.gp;
   const int row0 = m_block * 256;
   if (row0 >= rows_total) return;  // uniform for the whole CTA, nothing allocated yet
@@ -198,7 +219,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
 
   // register re-distribution (per warpgroup): softmax rows live in registers, the MMA/TMA warps need few
   if (warp >= 8) {
-  reg_dealloc<80>();
+  reg_dealloc<Cfg::kRegsOther>();
   // ================================================================== TMA producer
   if (warp == 9) {
     if (nblocks > 0 && elect_one()) {
@@ -208,13 +229,13 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         const int qpos0 = q_off + (row0 + i * 128) / p.gp;
 #pragma unroll
         for (int pn = 0; pn < Cfg::kPanels; ++pn)
-          tma_load_5d(sQ + i * Cfg::kTileBytes + pn * Cfg::kPanelBytes, &p.tm_q, bar_q_full(i), pn * 64, 0, qpos0,
+          tma_load_5d(sQ + i * Cfg::kTileBytes + pn * Cfg::kPanelBytes, &p.tm_q, bar_q_full(i), pn * Cfg::kPanelElems, 0, qpos0,
                       slot, bq);
       }
       int ring = 0;  // running slot counter: K_it -> 2*it, V_it -> 2*it + 1
       for (int it = 0; it < nblocks; ++it) {
         const int j = n_max - 1 - it;
-        int row = k_off + j * 128, c3 = p.cu_seqlens_k ? 0 : bidb;
+        int row = k_off + j * 128, c3 = p.cu_seqlens_k ? 0 : (p.cache_batch_idx ? p.cache_batch_idx[bidb] : bidb);
         if (p.page_size) {
           const int pos = j * 128;
           c3 = p.block_table[bidb * p.block_table_batch_stride + pos / p.page_size];
@@ -229,7 +250,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           const CUtensorMap* tm = kv == 0 ? &p.tm_k : &p.tm_v;
 #pragma unroll
           for (int pn = 0; pn < Cfg::kPanels; ++pn)
-            tma_load_4d(sKV + s * Cfg::kTileBytes + pn * Cfg::kPanelBytes, tm, bar_kv_full(s), pn * 64, row, hk_idx,
+            tma_load_4d(sKV + s * Cfg::kTileBytes + pn * Cfg::kPanelBytes, tm, bar_kv_full(s), pn * Cfg::kPanelElems, row, hk_idx,
                         c3);
         }
       }
@@ -255,17 +276,19 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         const uint32_t la = lo_of(sQ + i * Cfg::kTileBytes) | uint32_t(desc_k_major);
         const uint32_t lb = lo_of(sKV + slot_k * Cfg::kTileBytes) | uint32_t(desc_k_major);
 #pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk) {
+        for (int kk = 0; kk < kD * kBytes / 32; ++kk) {  // one MMA per 32 bytes of the head dimension
           const uint32_t off = ((kk / 4) * Cfg::kPanelBytes + (kk % 4) * 32) >> 4;
-          mma_ss<false>(tS[i], mk(hi_k, la + off), mk(hi_k, lb + off), idesc_qk, kk > 0);
+          mma_ss<kFp8>(tS[i], mk(hi_k, la + off), mk(hi_k, lb + off), idesc_qk, kk > 0);
         }
       };
       auto issue_pv = [&](int i, int slot_v, bool acc, int half) {
         const uint32_t lb = lo_of(sKV + slot_v * Cfg::kTileBytes) | lo_mn;
+        constexpr int kSteps = 4 * kBytes;              // MMAs per 128 keys (K = 16 keys for 16-bit, 32 for fp8)
+        constexpr uint32_t kStepBytes = 4096 / kBytes;  // that many key rows of 128 B
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const int kk = half * 4 + k4;
-          mma_ts<false>(tO[i], tS[i] + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+        for (int k4 = 0; k4 < kSteps / 2; ++k4) {
+          const int kk = half * (kSteps / 2) + k4;
+          mma_ts<kFp8>(tO[i], tS[i] + kk * 8, mk(hi_mn, lb + kk * (kStepBytes >> 4)), idesc_pv, (acc || kk > 0) ? 1u : 0u);
         }
       };
 
@@ -329,7 +352,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   }
   } else {
   // ================================================================== softmax warpgroups
-    reg_alloc<216>();
+    reg_alloc<Cfg::kRegsSoftmax>();
     const int tile = warp >> 2;
     if (tile < ntiles) {
       const int wq = warp & 3;
@@ -340,7 +363,21 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       const int qpos = r / p.gp;
       const int head = slot * p.gp + (r - qpos * p.gp);
       const bool row_valid = r < rows_total;
-      const float scale_log2 = p.scale_log2;
+      // fp8: S = (q*qd).(k*kd) -> fold the de-scales into the softmax scale; O picks up vd in the epilogue
+      float descale_qk = 1.f, descale_v = 1.f;
+      if constexpr (kFp8) {
+        if (p.q_descale) descale_qk *= p.q_descale[bidb * p.q_descale_bs + hk_idx];
+        if (p.k_descale) descale_qk *= p.k_descale[bidb * p.k_descale_bs + hk_idx];
+        if (p.v_descale) descale_v = p.v_descale[bidb * p.v_descale_bs + hk_idx];
+      }
+      const bool has_softcap = p.softcap_pre != 0.f;
+      const float softcap_pre = p.softcap_pre * descale_qk;
+      const float scale_eff = has_softcap ? p.scale : p.scale * descale_qk;       // natural-log scale of the raw scores
+      const float scale_log2 = has_softcap ? p.scale_log2 : p.scale_log2 * descale_qk;
+      // P is written as exp2(x - m + kPOffset): e4m3 keeps 2^-9..448, so fp8 shifts P up by 2^8 (removed again by
+      // the normaliser) and may not let the reference max lag (a lag of t would allow P up to 2^(8+t) > 448)
+      constexpr float kPOffset = kFp8 ? 8.0f : 0.0f;
+      constexpr float kLagLog2 = kFp8 ? 0.0f : 8.0f;
       // tile-level limits for the "does this block need masking" test
       const int t_row_lo = row0 + tile * 128;
       int t_row_hi = t_row_lo + 127 < rows_total - 1 ? t_row_lo + 127 : rows_total - 1;
@@ -350,7 +387,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       if (p.has_right) { int l = qpos + 1 + shift + p.wr; col_hi = l < col_hi ? l : col_hi; }
       if (p.has_left) { int l = qpos + shift - p.wl; col_lo = l > 0 ? l : 0; }
       float slope = 0.f;
-      if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + head] / p.scale;
+      if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + head] / scale_eff;
 
       float m_ref = kNegInf, row_sum = 0.f;
       for (int it = 0; it < nblocks; ++it) {
@@ -364,7 +401,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         bool need_mask = col0 + 128 > sk_b;
         if (p.has_right) need_mask |= col0 + 128 > t_qlo + 1 + shift + p.wr;
         if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
-        const bool slow = need_mask || p.softcap_pre != 0.f || p.alibi_slopes != nullptr ||
+        const bool slow = need_mask || has_softcap || p.alibi_slopes != nullptr ||
                           (p.debug_s != nullptr && it == 0);
         float mx;
         if (!slow) {
@@ -404,9 +441,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
 #pragma unroll
             for (int c = 0; c < 128; ++c) p.debug_s[(wq * 32 + lane) * 128 + c] = s[c];
           }
-          if (p.softcap_pre != 0.f) {
+          if (has_softcap) {
 #pragma unroll
-            for (int c = 0; c < 128; ++c) s[c] = tanh_approx(s[c] * p.softcap_pre);
+            for (int c = 0; c < 128; ++c) s[c] = tanh_approx(s[c] * softcap_pre);
           }
           if (p.alibi_slopes) {  // bias = -slope * |i + sk - sq - j|  (mask.h:148-165)
             const float rel0 = float(qpos + shift - col0);
@@ -431,7 +468,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         if (it == 0) {
           m_ref = m_new;
         } else {
-          bool need = (m_new - m_ref) * scale_log2 > 8.0f;  // NaN (-inf - -inf) compares false
+          bool need = (m_new - m_ref) * scale_log2 > kLagLog2;  // NaN (-inf - -inf) compares false
           if (m_ref == kNegInf) {  // nothing accumulated yet for this row: O row is 0, sum is 0
             m_ref = m_new;
             need = false;
@@ -453,7 +490,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
             if (need) m_ref = m_new;
           }
         }
-        const float neg_ms = (m_ref == kNegInf) ? 0.f : -m_ref * scale_log2;
+        const float neg_ms = (m_ref == kNegInf) ? kPOffset : kPOffset - m_ref * scale_log2;
         // ---- P = exp2(S*scale_log2 - m*scale_log2), written back over S as packed 16-bit.
         // Packed FFMA2 for the scaling; kPolyPairs of every 4 pairs take the FMA-pipe polynomial instead
         // of MUFU.EX2 (the MUFU unit, 16 op/clk/SM, is otherwise as busy as the tensor pipe).
@@ -462,6 +499,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
 #pragma unroll
         for (int cc = 0; cc < 128; cc += 32) {
           uint32_t pk[16];
+          float ee[4];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             float x0, x1, e0, e1;
@@ -474,9 +512,16 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             if (c & 2) acc_b = add2(acc_b, pack2(e0, e1));
             else acc_a = add2(acc_a, pack2(e0, e1));
-            pk[c / 2] = Elt<T>::pack(e0, e1);
+            if constexpr (kFp8) {
+              ee[c & 2] = e0;
+              ee[(c & 2) + 1] = e1;
+              if (c & 2) pk[c / 4] = pack_e4m3x4(ee[0], ee[1], ee[2], ee[3]);
+            } else {
+              pk[c / 2] = Elt<T>::pack(e0, e1);
+            }
           }
-          tmem_st_x16(tS + cc / 2, pk);
+          if constexpr (kFp8) tmem_st_x8(tS + cc / 4, pk);
+          else tmem_st_x16(tS + cc / 2, pk);
           if (cc == 32 || cc == 96) {  // half of P is in TMEM: let the first / second half of P V start
             tmem_wait_st();
             tc_fence_before();
@@ -496,8 +541,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       float inv = 0.f, lse_val;
       const bool dead = !(row_sum > 0.f);  // also catches NaN
       if (!dead) {
-        inv = 1.0f / row_sum;
-        lse_val = m_ref * p.scale + __logf(row_sum);
+        inv = descale_v / row_sum;
+        lse_val = m_ref * scale_eff + __logf(row_sum) - kPOffset * 0.6931471805599453f;
       } else {
         // fully masked row: +inf for a final result, -inf for a split partial
         // (softmax.h:180, flash_fwd_kernel.h:544-582)
@@ -531,7 +576,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         }
         if (row_valid) p.lse_accum[prow] = lse_val;
       } else {
-        T* dst = reinterpret_cast<T*>(p.o) + (p.cu_seqlens_q ? 0 : bidb * p.o_batch_stride) +
+        OutT* dst = reinterpret_cast<OutT*>(p.o) + (p.cu_seqlens_q ? 0 : bidb * p.o_batch_stride) +
                  int64_t(q_off + qpos) * p.o_row_stride + int64_t(head) * p.o_head_stride;
 #pragma unroll
         for (int cc = 0; cc < kD; cc += 32) {

@@ -63,14 +63,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
 #if FA_SPIN_GUARD
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("[fa_b200] mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, parity);
-      __trap();
+    if ((++spins & 1023u) == 0) {  // wall-clock bound (2 s): a starved barrier is a protocol bug, say which one
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) {
+        printf("[fa_b200] mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 #else

@@ -121,6 +121,56 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
     return [out, lse, p, rng_state]
 
 
+# --------------------------------------------------------------------------------------- fwd_fp8
+def fwd_fp8(q, k, v, out_, q_descale, k_descale, v_descale, softmax_scale, is_causal, window_size_left,
+            window_size_right, softcap=0.0, alibi_slopes_=None, num_splits=0) -> List[torch.Tensor]:
+    """FP8 e4m3 forward (no FA2 equivalent: flash_api.cpp:396 rejects fp8; spec = FA3 `mha_fwd` descale
+    arguments, hopper/flash_api.cpp, and flash_attn/cute/interface.py:637-643).  q/k/v torch.float8_e4m3fn,
+    descales (b, h_k) fp32 or None (= 1.0); output bf16 -> [out, softmax_lse(b,h,sq)]."""
+    lib = _lib.load()
+    f8 = torch.float8_e4m3fn
+    _check(q.is_cuda and k.is_cuda and v.is_cuda, "Input tensor must be on CUDA device")
+    _check(q.dtype == f8 and k.dtype == f8 and v.dtype == f8, "fwd_fp8 expects float8_e4m3fn q, k, v")
+    _check(q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Input tensor must have contiguous last dimension")
+    b, sq, h, d = q.shape
+    sk, hk = k.shape[1], k.shape[2]
+    _check(d % 16 == 0 and d <= 128, "fp8 forward supports head dimensions that are multiples of 16 up to 128")
+    _check(h % hk == 0, "Number of heads in key/value must divide number of heads in query")
+    out = out_ if out_ is not None else torch.empty((b, sq, h, d), dtype=torch.bfloat16, device=q.device)
+    _check(out.dtype == torch.bfloat16 and out.stride(-1) == 1 and tuple(out.shape) == (b, sq, h, d), "out must be bf16 (b,sq,h,d)")
+    lse = torch.empty((b, h, sq), dtype=torch.float32, device=q.device)
+    if sq == 0:
+        return [out, lse]
+    if sk == 0:
+        out.zero_()
+        lse.fill_(float("inf"))
+        return [out, lse]
+    a = _lib.FwdArgs()
+    a.q, a.k, a.v, a.out, a.softmax_lse = _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse)
+    a.q_batch_stride, a.q_row_stride, a.q_head_stride = q.stride(0), q.stride(1), q.stride(2)
+    a.k_batch_stride, a.k_row_stride, a.k_head_stride = k.stride(0), k.stride(1), k.stride(2)
+    a.v_batch_stride, a.v_row_stride, a.v_head_stride = v.stride(0), v.stride(1), v.stride(2)
+    a.o_batch_stride, a.o_row_stride, a.o_head_stride = out.stride(0), out.stride(1), out.stride(2)
+    a.b, a.seqlen_q, a.seqlen_k, a.h, a.h_k, a.d = b, sq, sk, h, hk, d
+    a.dtype = _lib.FP8_E4M3
+    keep = []
+    for name, t in (("q_descale", q_descale), ("k_descale", k_descale), ("v_descale", v_descale)):
+        if t is not None:
+            _check(t.dtype == torch.float32 and t.is_cuda and tuple(t.shape) == (b, hk), f"{name} must be fp32 (batch, nheads_k)")
+            t = t.contiguous()
+            keep.append(t)
+            setattr(a, name, _ptr(t))
+            setattr(a, name + "_batch_stride", t.stride(0))
+    a.softmax_scale, a.softcap = softmax_scale, softcap
+    a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
+    a.num_splits = num_splits
+    _alibi(a, alibi_slopes_, b, h)
+    with torch.cuda.device(q.device):
+        ws = _workspace(lib, a, q.device)  # noqa: F841
+        _lib.check(lib.fa_b200_mha_fwd(C.byref(a), _stream(q)))
+    return [out, lse]
+
+
 # --------------------------------------------------------------------------------------- varlen_fwd
 def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_, block_table_, alibi_slopes_,
                max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal, window_size_left,
@@ -209,9 +259,6 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
     (num_blocks,page,h_k,d) -> [out, softmax_lse(b,h,sq)]."""
     lib = _lib.load()
     _common_checks(q, kcache, vcache)
-    _check(rotary_cos_ is None and rotary_sin_ is None, "fa_b200: fused rotary in fwd_kvcache is not implemented")
-    _check(cache_batch_idx_ is None, "fa_b200: cache_batch_idx is not implemented")
-    _check(leftpad_k_ is None, "fa_b200: leftpad_k is not implemented")
     b, sq, h, d = q.shape
     paged = block_table_ is not None
     if paged:
@@ -221,7 +268,7 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
         _check(page % 256 == 0, "Paged KV cache block size must be divisible by 256")
         sk = block_table_.shape[1] * page
     else:
-        _check(kcache.shape[0] == b, "fa_b200: kcache batch must equal q batch (cache_batch_idx not implemented)")
+        _check(cache_batch_idx_ is not None or kcache.shape[0] == b, "kcache batch must equal q batch unless cache_batch_idx is given")
         sk, hk = kcache.shape[1], kcache.shape[2]
         num_pages, page = 0, 0
     _check(d <= 256, "FlashAttention forward only supports head dimension at most 256")
@@ -230,13 +277,29 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
     if seqlens_k_ is not None:
         _check(seqlens_k_.dtype == torch.int32, "seqlens_k must have dtype int32")
         _check(seqlens_k_.is_cuda and seqlens_k_.is_contiguous() and seqlens_k_.numel() == b, "seqlens_k must be (batch,) contiguous cuda")
+    for name, t in (("cache_batch_idx", cache_batch_idx_), ("leftpad_k", leftpad_k_)):
+        if t is not None:
+            _check(t.dtype == torch.int32 and t.is_cuda and t.is_contiguous() and t.numel() == b, f"{name} must be (batch,) int32 contiguous cuda")
+            _check(not paged, "We don't support Paged KV and leftpad_k / cache_batch_idx running at the same time yet")
+    if leftpad_k_ is not None:
+        _check(seqlens_k_ is not None, "leftpad_k requires seqlens_k")
+    if rotary_cos_ is not None:
+        _check(k_ is not None, "If rotary cos/sin are provided, new key / value to be appended to KV cache must also be provided")
+        _check(rotary_sin_ is not None and rotary_cos_.dtype == q.dtype and rotary_sin_.dtype == q.dtype, "rotary_cos/sin must have the same dtype as query")
+        _check(rotary_cos_.is_contiguous() and rotary_sin_.is_contiguous(), "rotary_cos/sin must be contiguous")
+        _check((rotary_cos_.shape[-1] * 2) % 16 == 0 and rotary_cos_.shape[-1] * 2 <= d, "Only rotary dimensions divisible by 16 are currently supported")
     if k_ is not None:
         # append new keys/values into the cache at position cache_seqlens (flash_fwd_kernel.h:691-790)
         _check(v_ is not None, "If key is supplied, value must also be passed in")
         _check(seqlens_k_ is not None, "If key is supplied, seqlens_k must also be passed in")
-        from .kvcache_ops import append_kv
+        _check(k_.dtype == q.dtype and v_.dtype == q.dtype, "Key and value must have the same dtype as query")
+        _check(k_.stride(-1) == 1 and v_.stride(-1) == 1, "Key / value tensor must have contiguous last dimension")
+        from .kvcache_ops import append_kv_rotary
 
-        append_kv(kcache, vcache, k_, v_, seqlens_k_, block_table_)
+        # query i is rotated at cache_seqlens + i when causal or local, else all queries at cache_seqlens
+        local = window_size_left >= 0 or window_size_right >= 0
+        q = append_kv_rotary(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_, cache_batch_idx_,
+                             leftpad_k_, block_table_, is_rotary_interleaved, bool(is_causal) or local)
         seqlens_eff = seqlens_k_ + k_.shape[1]
     else:
         seqlens_eff = seqlens_k_
@@ -261,6 +324,7 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
     if seqlens_eff is not None:
         seqlens_eff = seqlens_eff.contiguous()
         a.seqused_k = _ptr(seqlens_eff)
+    a.cache_batch_idx, a.leftpad_k = _ptr(cache_batch_idx_), _ptr(leftpad_k_)
     a.softmax_scale, a.softcap = softmax_scale, softcap
     a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
     a.num_splits = num_splits

@@ -74,9 +74,18 @@ class _FlashAttnVarlenFunc(torch.autograd.Function):
 
 
 def flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
-                    alibi_slopes=None, deterministic=False, return_attn_probs=False):
+                    alibi_slopes=None, deterministic=False, return_attn_probs=False, q_descale=None, k_descale=None,
+                    v_descale=None):
     """q (b, sq, h, d), k/v (b, sk, h_k, d) -> out (b, sq, h, d) [, softmax_lse (b, h, sq), S_dmask].
-    Causal / sliding-window masks are aligned to the bottom-right corner when sq != sk."""
+    Causal / sliding-window masks are aligned to the bottom-right corner when sq != sk.
+    float8_e4m3fn inputs (forward only, FA3-style `*_descale` (b, h_k) fp32 factors) return bf16."""
+    if q.dtype == torch.float8_e4m3fn:
+        assert dropout_p == 0.0, "fp8 forward has no dropout"
+        if softmax_scale is None:
+            softmax_scale = q.shape[-1] ** (-0.5)
+        out, lse = _op.fwd_fp8(_c(q), _c(k), _c(v), None, q_descale, k_descale, v_descale, softmax_scale, causal,
+                               window_size[0], window_size[1], softcap, alibi_slopes)
+        return (out, lse, None) if return_attn_probs else out
     return _FlashAttnFunc.apply(q, k, v, dropout_p, softmax_scale, causal, tuple(window_size), softcap, alibi_slopes,
                                 deterministic, return_attn_probs)
 

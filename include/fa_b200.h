@@ -65,6 +65,8 @@ typedef struct fa_b200_fwd_args {
   const int32_t* cu_seqlens_q; /* (b+1) or NULL */
   const int32_t* cu_seqlens_k; /* (b+1) or NULL */
   const int32_t* seqused_k;    /* (b) or NULL: number of valid keys per batch (cache_seqlens) */
+  const int32_t* cache_batch_idx; /* (b) or NULL: batch b reads cache row cache_batch_idx[b] (kvcache, not paged) */
+  const int32_t* leftpad_k;    /* (b) or NULL: keys of batch b start at row leftpad_k[b] (kvcache, not paged) */
   const int32_t* block_table;  /* (b, max_blocks_per_seq) or NULL */
   int64_t block_table_batch_stride;
   int32_t page_block_size;     /* multiple of 128 (reference requires 256: flash_api.cpp:1305) */
@@ -129,6 +131,26 @@ size_t fa_b200_bwd_workspace_bytes(const fa_b200_bwd_args* args);
 int fa_b200_fwd_combine(const float* o_partial, const float* lse_partial, void* out, float* lse,
                         int32_t num_splits, int64_t rows, int32_t d, int32_t dtype,
                         fa_b200_stream_t stream);
+
+/* ---- decode prologue: append k/v into the cache (+ rotary on the new keys and on q), in place
+ *      (mha_fwd_kvcache's knew/vnew/rotary_cos/rotary_sin arguments, flash_api.cpp:1243-1264, flash_fwd_kernel.h:691-828) */
+typedef struct fa_b200_append_args {
+  void* kcache; void* vcache;           /* (b_c, sk, h_k, d) | paged (num_pages, page, h_k, d) */
+  const void* knew; const void* vnew;   /* (b, s_new, h_k, d) */
+  const void* q; void* q_out;           /* (b, sq, h, d): q_out receives the rotated q (NULL without rotary) */
+  int64_t kc_batch_stride, kc_row_stride, kc_head_stride, vc_batch_stride, vc_row_stride, vc_head_stride;
+  int64_t kn_batch_stride, kn_row_stride, kn_head_stride, vn_batch_stride, vn_row_stride, vn_head_stride;
+  int64_t q_batch_stride, q_row_stride, q_head_stride, qo_batch_stride, qo_row_stride, qo_head_stride;
+  const int32_t* cache_seqlens;         /* (b) lengths BEFORE the append */
+  const int32_t* cache_batch_idx; const int32_t* leftpad_k;
+  const int32_t* block_table; int64_t block_table_batch_stride; int32_t page_block_size;
+  const void* rotary_cos; const void* rotary_sin; /* (seqlen_ro, rotary_dim/2), dtype of q, or NULL */
+  int32_t rotary_dim; int32_t is_rotary_interleaved;
+  int32_t q_pos_per_row;                /* 1: query i is rotated at cache_seqlens+i (causal/local); 0: all at cache_seqlens */
+  int32_t b, seqlen_new, seqlen_q, h, h_k, d, dtype;
+} fa_b200_append_args;
+int fa_b200_kvcache_append(const fa_b200_append_args* args, fa_b200_stream_t stream);
+size_t fa_b200_sizeof_append_args(void);
 
 /* ---- helpers ---- */
 int fa_b200_num_splits_heuristic(int batch_nheads_mblocks, int num_sms, int num_n_blocks, int max_splits);

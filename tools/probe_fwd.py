@@ -191,3 +191,47 @@ if __name__ == "__main__":
     globals()["stage_" + st]()
     torch.cuda.synchronize()
     print("==== stage", st, "done", flush=True)
+
+
+def stage_fp8():
+    from oracle.attention_oracle import attention_oracle
+    f8 = torch.float8_e4m3fn
+    for name, b, sq, sk, h, hk, causal, window, desc in (
+        ("fp8 1tile", 1, 128, 128, 1, 1, False, (-1, -1), False),
+        ("fp8 multi", 2, 384, 640, 4, 2, False, (-1, -1), True),
+        ("fp8 causal", 1, 512, 512, 2, 2, True, (-1, -1), True),
+        ("fp8 window", 1, 1024, 1024, 2, 2, True, (256, 0), False),
+        ("fp8 ragged", 2, 200, 333, 3, 3, False, (-1, -1), True),
+    ):
+        q, k, v = make_qkv(b, sq, sk, h, hk, 128)
+        q8, k8, v8 = q.to(f8), k.to(f8), v.to(f8)
+        qd = (torch.rand(b, hk, device="cuda") + 0.5).float() if desc else None
+        kd = (torch.rand(b, hk, device="cuda") + 0.5).float() if desc else None
+        vd = (torch.rand(b, hk, device="cuda") + 0.5).float() if desc else None
+        out, lse, _ = fab.flash_attn_func(q8, k8, v8, causal=causal, window_size=window, return_attn_probs=True,
+                                         q_descale=qd, k_descale=kd, v_descale=vd)
+        torch.cuda.synchronize()
+        c = lambda t: None if t is None else t.cpu()
+        kw = dict(causal=causal, window=window, q_descale=c(qd), k_descale=c(kd), v_descale=c(vd))
+        ref, lse_ref = attention_oracle(q8.cpu().float(), k8.cpu().float(), v8.cpu().float(), **kw)
+        refq, _ = attention_oracle(q8.cpu().float(), k8.cpu().float(), v8.cpu().float(), p_dtype=f8, **kw)
+        e = (out.float().cpu() - ref).abs().max().item()
+        eq = (refq - ref).abs().max().item()
+        fin = torch.isfinite(lse_ref)
+        print(f"[{name}] err={e:.3e} (e4m3-P oracle err {eq:.3e}) ref_max={ref.abs().max().item():.2f} "
+              f"lse_err={(lse.cpu()[fin] - lse_ref[fin]).abs().max().item():.2e} nan={torch.isnan(out).any().item()}", flush=True)
+    # timing: BASELINE C4 = fp8 fwd b1 h16 s32768 d128 window (4096, 0)
+    b, h, s = 1, 16, 32768
+    q = torch.randn(b, s, h, 128, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn_like(q); v = torch.randn_like(q)
+    for nm, tq in (("fp8", (q.to(f8), k.to(f8), v.to(f8))), ("bf16", (q, k, v))):
+        f = lambda: fab.flash_attn_func(*tq, causal=True, window_size=(4096, 0))
+        for _ in range(3): f()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(10): f()
+        ev[1].record(); torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 10
+        pairs = sum(min(i, 4096) + 1 for i in range(s))
+        print(f"[time C4 {nm}] {ms:.3f} ms {4 * b * h * pairs * 128 / ms / 1e9:.1f} TFLOP/s", flush=True)
