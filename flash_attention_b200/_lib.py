@@ -29,7 +29,7 @@ class FwdArgs(C.Structure):
         ("o_batch_stride", _i64), ("o_row_stride", _i64), ("o_head_stride", _i64),
         ("b", _i32), ("seqlen_q", _i32), ("seqlen_k", _i32), ("h", _i32), ("h_k", _i32), ("d", _i32),
         ("total_q", _i32), ("total_k", _i32),
-        ("dtype", _i32),
+        ("dtype", _i32), ("b_kvcache", _i32),
         ("cu_seqlens_q", _vp), ("cu_seqlens_k", _vp), ("seqused_k", _vp),
         ("cache_batch_idx", _vp), ("leftpad_k", _vp), ("block_table", _vp),
         ("block_table_batch_stride", _i64),

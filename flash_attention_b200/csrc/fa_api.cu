@@ -238,7 +238,7 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     uint64_t rows, nb;
     if (a.block_table) { rows = a.page_block_size; nb = a.num_pages; }
     else if (a.cu_seqlens_k) { rows = a.total_k; nb = 1; }
-    else { rows = a.seqlen_k; nb = a.b; }
+    else { rows = a.seqlen_k; nb = a.b_kvcache > 0 ? a.b_kvcache : a.b; }
     uint64_t dims[4] = {uint64_t(a.d), rows, uint64_t(a.h_k), nb};
     uint64_t str[3] = {uint64_t(rs) * esz, uint64_t(hs) * esz, uint64_t(bs) * esz};
     if (nb == 1) str[2] = rows * str[0];

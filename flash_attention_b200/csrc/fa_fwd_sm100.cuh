@@ -106,7 +106,7 @@ template <> struct EltInfo<fp8_e4m3> { static constexpr int kBytes = 1; static c
 __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 #ifndef FA_FWD_POLY_PAIRS
-#define FA_FWD_POLY_PAIRS 2
+#define FA_FWD_POLY_PAIRS 1  // measured on B200 (r01): 0 -> 1315, 1 -> 1339, 2 -> 1307, 3 -> 1147, 4 -> 1046 TFLOP/s fwd
 #endif
 
 template <typename T, int kD>

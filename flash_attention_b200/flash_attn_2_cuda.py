@@ -325,6 +325,7 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
         seqlens_eff = seqlens_eff.contiguous()
         a.seqused_k = _ptr(seqlens_eff)
     a.cache_batch_idx, a.leftpad_k = _ptr(cache_batch_idx_), _ptr(leftpad_k_)
+    a.b_kvcache = 0 if paged else kcache.shape[0]
     a.softmax_scale, a.softcap = softmax_scale, softcap
     a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
     a.num_splits = num_splits

@@ -61,6 +61,7 @@ typedef struct fa_b200_fwd_args {
   int32_t b, seqlen_q, seqlen_k, h, h_k, d;  /* varlen: seqlen_* are the max_seqlen_* arguments */
   int32_t total_q, total_k;                  /* varlen only (rows of the packed tensors), else 0 */
   int32_t dtype;                             /* enum fa_b200_dtype */
+  int32_t b_kvcache;                         /* kvcache with cache_batch_idx: batch extent of k/v (0 = same as b) */
   /* varlen / kvcache metadata (device pointers, int32) */
   const int32_t* cu_seqlens_q; /* (b+1) or NULL */
   const int32_t* cu_seqlens_k; /* (b+1) or NULL */

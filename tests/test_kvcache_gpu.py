@@ -54,8 +54,9 @@ def test_decode_cache_seqlens(fab, paged, num_splits):
     else:
         kc = torch.randn(b, nblk * page, hk, d, device="cuda", dtype=torch.bfloat16)
         vc = torch.randn(b, nblk * page, hk, d, device="cuda", dtype=torch.bfloat16)
-        kc[:, 1400:] = float("nan")  # garbage beyond the valid length must not leak (0 * NaN)
-        vc[0, 700:] = float("nan")
+        for i in range(b):  # garbage beyond each batch's valid length must not leak (0 * NaN)
+            kc[i, int(seqlens[i]):] = float("nan")
+            vc[i, int(seqlens[i]):] = float("nan")
         kd, vd = kc.cpu(), vc.cpu()
         out, lse = fab.flash_attn_with_kvcache(q, kc, vc, cache_seqlens=seqlens, num_splits=num_splits, return_softmax_lse=True)
     kd, vd = torch.nan_to_num(kd), torch.nan_to_num(vd)

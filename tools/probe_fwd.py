@@ -185,12 +185,6 @@ def stage_time():
         print(f"[time] b{b} h{h}/{hk} s{s} causal={causal}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
-if __name__ == "__main__":
-    st = sys.argv[1]
-    print("==== stage", st, flush=True)
-    globals()["stage_" + st]()
-    torch.cuda.synchronize()
-    print("==== stage", st, "done", flush=True)
 
 
 def stage_fp8():
@@ -235,3 +229,11 @@ def stage_fp8():
         ms = ev[0].elapsed_time(ev[1]) / 10
         pairs = sum(min(i, 4096) + 1 for i in range(s))
         print(f"[time C4 {nm}] {ms:.3f} ms {4 * b * h * pairs * 128 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    st = sys.argv[1]
+    print("==== stage", st, flush=True)
+    globals()["stage_" + st]()
+    torch.cuda.synchronize()
+    print("==== stage", st, "done", flush=True)
