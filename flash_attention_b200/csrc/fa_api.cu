@@ -47,7 +47,7 @@ static EncodeTiledFn get_encode_fn() {
 // rank-N tiled tensor map, 128-byte swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES
 // for dims 1..rank-1.
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box) {
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   cuuint64_t gdim[5], gstr[4];
@@ -63,7 +63,8 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* ba
   }
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_error("tensor base pointers must be 16-byte aligned (TMA)");
   CUresult r = fn(out, dt, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
     snprintf(buf, sizeof buf,

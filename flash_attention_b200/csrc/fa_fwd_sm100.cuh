@@ -374,10 +374,13 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       const float softcap_pre = p.softcap_pre * descale_qk;
       const float scale_eff = has_softcap ? p.scale : p.scale * descale_qk;       // natural-log scale of the raw scores
       const float scale_log2 = has_softcap ? p.scale_log2 : p.scale_log2 * descale_qk;
-      // P is written as exp2(x - m + kPOffset): e4m3 keeps 2^-9..448, so fp8 shifts P up by 2^8 (removed again by
-      // the normaliser) and may not let the reference max lag (a lag of t would allow P up to 2^(8+t) > 448)
-      constexpr float kPOffset = kFp8 ? 8.0f : 0.0f;
-      constexpr float kLagLog2 = kFp8 ? 0.0f : 8.0f;
+      // P is written as exp2(x - m_ref + kPOffset) and the reference max m_ref may lag the true row max by up to
+      // kLagLog2 (exact after normalisation; avoids an O read-modify-write in TMEM on most blocks).  e4m3 keeps
+      // 2^-9 .. 448, so fp8 shifts P up by 2^5 and allows a lag of 2^3: P <= 2^8, and probabilities down to
+      // 2^-14 of the row max survive the cast (the reference scales by 2^8 with no lag, flash_fwd_sm100.py:2190;
+      // with a zero lag almost every block rescales: 32 rows per warp, each a new max with probability ~1/j).
+      constexpr float kPOffset = kFp8 ? 5.0f : 0.0f;
+      constexpr float kLagLog2 = kFp8 ? 3.0f : 8.0f;
       // tile-level limits for the "does this block need masking" test
       const int t_row_lo = row0 + tile * 128;
       int t_row_hi = t_row_lo + 127 < rows_total - 1 ? t_row_lo + 127 : rows_total - 1;
