@@ -18,7 +18,7 @@ static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 struct BwdPlan {
   int kD, sq_r;
   int has_left, has_right, wl, wr;
-  size_t off_lse, off_dps, off_dq, total;
+  size_t off_lse, off_dps, off_dq, off_sem, total;
 };
 
 static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
@@ -43,7 +43,8 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   pl->off_lse = 0;
   pl->off_dps = align256(stat);
   pl->off_dq = pl->off_dps + align256(stat);
-  pl->total = pl->off_dq + align256(stat * pl->kD);
+  pl->off_sem = pl->off_dq + align256(stat * pl->kD);   // deterministic mode: one counter per (b, h, query block),
+  pl->total = pl->off_sem + align256(stat / 128);        // placed right behind dq_accum so one memset clears both
   return 0;
 }
 
@@ -71,7 +72,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   float* dpsum = reinterpret_cast<float*>(ws + pl.off_dps);
   float* dq_accum = reinterpret_cast<float*>(ws + pl.off_dq);
   const int sq_r = pl.sq_r;
-  cudaError_t e = cudaMemsetAsync(dq_accum, 0, size_t(a.b) * a.h * sq_r * kD * sizeof(float), stream);
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, pl.total - pl.off_dq, stream);  // dq_accum + semaphores
   if (e != cudaSuccess) return set_error(std::string("cudaMemsetAsync(dq_accum): ") + cudaGetErrorString(e));
   {
     dim3 grid((sq_r + 7) / 8, a.h, a.b);
@@ -105,6 +106,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
     if (int rc = make_tmap(&kp.tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, dims, str, box)) return rc;
   }
   kp.lse_log2 = lse_log2;
+  kp.dq_semaphore = a.deterministic ? reinterpret_cast<int*>(ws + pl.off_sem) : nullptr;
   kp.dpsum = dpsum;
   kp.dk = a.dk; kp.dv = a.dv;
   kp.dk_batch_stride = a.dk_batch_stride; kp.dk_row_stride = a.dk_row_stride; kp.dk_head_stride = a.dk_head_stride;

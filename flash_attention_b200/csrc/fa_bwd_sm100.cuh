@@ -33,6 +33,7 @@ struct BwdKernelParams {
   CUtensorMap tm_k, tm_v;    // 4-D (d, rows, h_k, b)
   CUtensorMap tm_dq;         // 4-D (kD, sq_r, h, b) fp32, box (32, 128, 1, 1), 128B swizzle, reduce-add target
   const float* lse_log2;     // (b, h, sq_r)
+  int* dq_semaphore;         // deterministic mode: (b, h, sq_r/128) counters, zero-initialised; else nullptr
   const float* dpsum;        // (b, h, sq_r)
   void* dk;
   void* dv;
@@ -332,6 +333,26 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
       const int m = m_min + it % n_m;
       mbar_wait(bar(B_DQF), it & 1, 600);
       tc_fence_after();
+      // Deterministic mode (reference: flash_api.cpp:928-929 gives every key-block column its own dq_accum slice;
+      // FA4 orders the reduce-adds with semaphores, interface.py:2199-2209 -- same idea here): the key blocks that
+      // touch query block m add their dQ partials in ascending key-block order.
+      int* sem = nullptr;
+      int my_turn = 0;
+      if (p.dq_semaphore) {
+        sem = p.dq_semaphore + (int64_t(bidb) * p.h + hq) * (p.sq_r / 128) + m;
+        int n_lo = 0;
+        if (p.has_left) {
+          const int x = 128 * m - 127 + shift - p.wl;
+          n_lo = x <= 0 ? 0 : (x + 127) / 128;
+        }
+        my_turn = n_block - n_lo;
+        if (leader) {
+          int cur;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cur) : "l"(sem) : "memory");
+          } while (cur != my_turn);
+        }
+      }
 #pragma unroll
       for (int half = 0; half < kD / 64; ++half) {
         uint32_t v[64];
@@ -361,6 +382,12 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
             tma_store_commit();
           }
         }
+      }
+      if (sem && leader) {  // all reduce-adds of this iteration have been performed: pass the turn on
+        tma_store_wait<0>();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sem), "r"(my_turn + 1) : "memory");
       }
     }
     if (leader) tma_store_wait<0>();

@@ -120,3 +120,21 @@ def test_full_size_slice_vs_oracle(fab):
     sl = lambda t: t[bi:bi + 1, :n, hi:hi + 1].cpu()
     _, _, rdq, _, _ = attention_oracle_bwd(sl(q), sl(k), sl(v), sl(do), causal=True)
     assert (dq[bi:bi + 1, :n, hi:hi + 1].float().cpu() - rdq).abs().max().item() <= 3e-2 * max(1.0, rdq.abs().max().item())
+
+
+@pytest.mark.parametrize("causal,window", [(False, (-1, -1)), (True, (-1, -1)), (False, (200, 100))])
+def test_deterministic_backward_is_bitwise_reproducible(fab, causal, window):
+    """deterministic=True orders the dQ reduce-adds (reference: test_flash_attn_deterministic,
+    tests/test_flash_attn.py:2413-2438: repeated runs must be torch.equal)."""
+    b, sq, sk, h, hk, d = 2, 640, 900, 4, 2, 128
+    q, k, v = make_qkv(b, sq, sk, h, hk, d)
+    do = torch.randn(b, sq, h, d, device="cuda", dtype=torch.bfloat16)
+    g0 = _grads(fab, q, k, v, do, causal=causal, window=window, deterministic=True)
+    for _ in range(10):
+        g = _grads(fab, q, k, v, do, causal=causal, window=window, deterministic=True)
+        for a, c in zip(g0, g):
+            assert torch.equal(a, c)
+    tol = bwd_tolerances(q, k, v, do, causal=causal, window=window)
+    for name, g_ in zip(("dq", "dk", "dv"), g0):
+        ref, bound = tol[name]
+        assert (g_.float().cpu() - ref).abs().max().item() <= bound, name
