@@ -10,8 +10,9 @@ BASELINE configs[1]'s shape with the metric's fwd+bwd).  FLOP convention is the 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fwd_bwd|fwd] [--causal] [--impl reference]
 
   value     device-resident throughput (inputs already in HBM), CUDA events, max over ranks
-  e2e       the same step through the public API starting from pinned HOST buffers: H2D of q,k,v,dO and
-            D2H of out,dq,dk,dv inside the timed region
+  e2e       the same step through the public host-buffer API (flash_attention_b200.host_pipeline): pinned HOST
+            buffers in, H2D of q,k,v,dO and D2H of out,dq,dk,dv inside the timed region (3-stage pipeline over
+            the batch: upload | kernels | download)
   roofline  dominant kernel (backward main loop in fwd_bwd mode, forward kernel in fwd mode):
             algorithmic FLOPs / CUDA-event time vs the measured bf16 peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference: the PyTorch attention_ref restatement (oracle/) on the host cores,
@@ -248,29 +249,31 @@ def main():
     peaks, peak_src = load_peaks()
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = kern_flops / (kms * 1e-3) / 1e12
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        key = ("bwd" if mode == "fwd_bwd" else "fwd") + ("_causal" if causal else "_noncausal")
+        traffic = tr.get(key, {}).get("bytes")  # a number: dram read + write bytes per launch
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "tensor", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": f"bf16_tflops_sustained, {peak_src}",
                 "ms_per_launch": kms}
 
     # ---- e2e: host (pinned) buffers -> H2D -> public API -> D2H of out (+ grads)
     hq, hk_, hv, hdo = (torch.empty(t_.shape, dtype=t_.dtype).pin_memory() for t_ in (qd, kd, vd, do))
     for dst, src in ((hq, qd), (hk_, kd), (hv, vd), (hdo, do)):
         dst.copy_(src)
-    ho = torch.empty_like(hq)
-    hdq, hdk, hdv = torch.empty_like(hq), torch.empty_like(hk_), torch.empty_like(hv)
+    ho = torch.empty_like(hq).pin_memory()  # results land in pinned host memory too (pageable D2H is synchronous)
+    hdq, hdk, hdv = torch.empty_like(hq).pin_memory(), torch.empty_like(hk_).pin_memory(), torch.empty_like(hv).pin_memory()
+
+    from flash_attention_b200.host_pipeline import HostAttentionPipeline
+
+    # public host-buffer entry point: 3-stage pipeline over the batch (H2D | kernels | D2H on separate streams)
+    pipe = HostAttentionPipeline(b, s, s, h, hk, d, torch.bfloat16, dev, chunks=b, backward=(mode == "fwd_bwd"))
 
     def e2e_step():
-        q2 = hq.to(dev, non_blocking=True).requires_grad_(mode == "fwd_bwd")
-        k2 = hk_.to(dev, non_blocking=True).requires_grad_(mode == "fwd_bwd")
-        v2 = hv.to(dev, non_blocking=True).requires_grad_(mode == "fwd_bwd")
-        o2 = fab.flash_attn_func(q2, k2, v2, causal=causal)
-        if mode == "fwd_bwd":
-            do2 = hdo.to(dev, non_blocking=True)
-            o2.backward(do2)
-            hdq.copy_(q2.grad, non_blocking=True)
-            hdk.copy_(k2.grad, non_blocking=True)
-            hdv.copy_(v2.grad, non_blocking=True)
-        ho.copy_(o2.detach(), non_blocking=True)
+        pipe.run(hq, hk_, hv, hdo, ho, hdq, hdk, hdv, causal=causal)
 
     nbytes = lambda t_: t_.numel() * t_.element_size()
     h2d = nbytes(hq) + nbytes(hk_) + nbytes(hv) + (nbytes(hdo) if mode == "fwd_bwd" else 0)

@@ -1,0 +1,28 @@
+"""Host-buffer entry point (the call bench.py's e2e leg times): results must be bit-identical to the device API,
+because chunking over the batch does not change any per-(batch, head) computation."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_host_pipeline_matches_device_api():
+    import flash_attention_b200 as fab
+    from flash_attention_b200.host_pipeline import HostAttentionPipeline
+
+    b, s, h, hk, d = 4, 384, 4, 2, 128
+    pin = lambda *shape: torch.randn(*shape).bfloat16().pin_memory()
+    hq, hk_, hv, hdo = pin(b, s, h, d), pin(b, s, hk, d), pin(b, s, hk, d), pin(b, s, h, d)
+    ho, hdq = torch.empty_like(hq).pin_memory(), torch.empty_like(hq).pin_memory()
+    hdk, hdv = torch.empty_like(hk_).pin_memory(), torch.empty_like(hv).pin_memory()
+    pipe = HostAttentionPipeline(b, s, s, h, hk, d, torch.bfloat16, "cuda", chunks=b, backward=True)
+    for _ in range(2):  # second run re-uses the staging buffers
+        pipe.run(hq, hk_, hv, hdo, ho, hdq, hdk, hdv, causal=True)
+    torch.cuda.synchronize()
+    q, k, v = (t.cuda().requires_grad_(True) for t in (hq, hk_, hv))
+    out = fab.flash_attn_func(q, k, v, causal=True)
+    out.backward(hdo.cuda())
+    assert torch.equal(ho, out.detach().cpu())
+    assert torch.equal(hdk, k.grad.cpu()) and torch.equal(hdv, v.grad.cpu())
+    # dQ goes through fp32 atomics (TMA reduce-add) whose order may differ between runs
+    assert (hdq.float() - q.grad.float().cpu()).abs().max().item() < 2e-2
