@@ -117,6 +117,7 @@ def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path (oracle port), timed per step."""
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; the CPU arm may use every host core
     mode = args.mode
     cb, _ = cpu_baseline(args.causal, mode, budget_s=2.0)  # warm
     vals = []
