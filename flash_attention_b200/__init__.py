@@ -28,4 +28,8 @@ def __getattr__(attr):
         from . import flash_attn_interface as m
 
         return getattr(m, attr)
+    if attr == "flash_attn_3":  # FA3-style surface: flash_attention_b200.flash_attn_3.flash_attn_func(...)
+        from . import flash_attn_3_interface as m3
+
+        return m3
     raise AttributeError(attr)

@@ -30,7 +30,7 @@ class FwdArgs(C.Structure):
         ("b", _i32), ("seqlen_q", _i32), ("seqlen_k", _i32), ("h", _i32), ("h_k", _i32), ("d", _i32),
         ("total_q", _i32), ("total_k", _i32),
         ("dtype", _i32), ("b_kvcache", _i32),
-        ("cu_seqlens_q", _vp), ("cu_seqlens_k", _vp), ("seqused_k", _vp),
+        ("cu_seqlens_q", _vp), ("cu_seqlens_k", _vp), ("seqused_k", _vp), ("seqused_q", _vp),
         ("cache_batch_idx", _vp), ("leftpad_k", _vp), ("block_table", _vp),
         ("block_table_batch_stride", _i64),
         ("page_block_size", _i32), ("num_pages", _i32),
@@ -39,7 +39,7 @@ class FwdArgs(C.Structure):
         ("is_causal", _i32), ("window_size_left", _i32), ("window_size_right", _i32),
         ("q_descale", _vp), ("k_descale", _vp), ("v_descale", _vp),
         ("q_descale_batch_stride", _i64), ("k_descale_batch_stride", _i64), ("v_descale_batch_stride", _i64),
-        ("num_splits", _i32),
+        ("num_splits", _i32), ("pack_gqa", _i32),
         ("workspace", _vp), ("workspace_bytes", _sz),
         ("debug_s", _vp),
     ]
@@ -97,6 +97,7 @@ SYMBOLS = {
     "fa_b200_mha_fwd_kvcache": (C.c_int, [C.POINTER(FwdArgs), _vp]),
     "fa_b200_fwd_workspace_bytes": (_sz, [C.POINTER(FwdArgs)]),
     "fa_b200_fwd_num_splits": (C.c_int, [C.POINTER(FwdArgs)]),
+    "fa_b200_fwd_plan": (C.c_int, [C.POINTER(FwdArgs), C.POINTER(C.c_int32)]),
     "fa_b200_mha_bwd": (C.c_int, [C.POINTER(BwdArgs), _vp]),
     "fa_b200_mha_varlen_bwd": (C.c_int, [C.POINTER(BwdArgs), _vp]),
     "fa_b200_bwd_workspace_bytes": (_sz, [C.POINTER(BwdArgs)]),

@@ -124,7 +124,6 @@ struct FwdPlan {
 static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   if (a.dtype != FA_B200_FP16 && a.dtype != FA_B200_BF16 && a.dtype != FA_B200_FP8_E4M3)
     return set_error("FlashAttention only support fp16, bf16 and fp8 e4m3 (forward) data type");
-  if (!a.q || !a.k || !a.v || !a.out || !a.softmax_lse) return set_error("q, k, v, out, softmax_lse must be non-null");
   if (a.b <= 0) return set_error("batch size must be positive");
   if (a.d <= 0 || a.d > 256) return set_error("FlashAttention forward only supports head dimension at most 256");
   if (a.d % 8 != 0) return set_error("head_size should be a multiple of 8");
@@ -158,7 +157,10 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   // 256 query positions would otherwise be mostly empty (decode / short queries).
   const int g = a.h / a.h_k;
   int gp = 1;
-  if (g > 1 && is_pow2(g) && g <= 128) {
+  if (a.pack_gqa == 1 && g > 1) {
+    if (!is_pow2(g) || g > 128) return set_error("pack_gqa needs a power-of-two group size <= 128");
+    gp = g;
+  } else if (a.pack_gqa == 0 && g > 1 && is_pow2(g) && g <= 128) {
     const int sq = a.seqlen_q;
     const double eff_unpacked = double(sq) / (cdiv(sq, 256) * 256);
     const double eff_packed = double(sq) * g / (cdiv(sq * g, 256) * 256);
@@ -217,6 +219,7 @@ static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t 
 
 static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream) {
   FwdPlan pl;
+  if (!a.q || !a.k || !a.v || !a.out || !a.softmax_lse) return set_error("q, k, v, out, softmax_lse must be non-null");
   if (int rc = plan_fwd(a, mode, &pl)) return rc;
   if (pl.num_splits > 1 && (!a.workspace || a.workspace_bytes < pl.ws_bytes))
     return set_error("workspace too small for split-KV (query fa_b200_fwd_workspace_bytes)");
@@ -265,6 +268,7 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   kp.cu_seqlens_q = a.cu_seqlens_q;
   kp.cu_seqlens_k = a.cu_seqlens_k;
   kp.seqused_k = a.seqused_k;
+  kp.seqused_q = a.seqused_q;
   kp.cache_batch_idx = a.cache_batch_idx;
   kp.leftpad_k = a.leftpad_k;
   kp.block_table = a.block_table;
@@ -357,6 +361,14 @@ size_t fa_b200_fwd_workspace_bytes(const fa_b200_fwd_args* args) {
   FwdPlan pl;
   if (!args || plan_fwd(*args, mode_of(args), &pl)) return 0;
   return pl.ws_bytes;
+}
+
+int fa_b200_fwd_plan(const fa_b200_fwd_args* args, int32_t out[3]) {
+  FwdPlan pl;
+  if (!args || !out) return set_error("null args");
+  if (int rc = plan_fwd(*args, mode_of(args), &pl)) return rc;
+  out[0] = pl.num_splits; out[1] = pl.gp; out[2] = pl.num_m_blocks;
+  return 0;
 }
 
 int fa_b200_fwd_num_splits(const fa_b200_fwd_args* args) {

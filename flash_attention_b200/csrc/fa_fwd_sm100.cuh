@@ -37,6 +37,7 @@ struct FwdKernelParams {
   const int* cu_seqlens_q;
   const int* cu_seqlens_k;
   const int* seqused_k;
+  const int* seqused_q;        // valid queries per batch (rows beyond are neither computed nor written)
   const int* cache_batch_idx;  // kvcache: batch b reads cache row cache_batch_idx[b]
   const int* leftpad_k;        // kvcache: first valid key row of batch b
   const int* block_table;
@@ -131,6 +132,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
   if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
   if (p.seqused_k) sk_b = p.seqused_k[bidb];
+  if (p.seqused_q) sq_b = p.seqused_q[bidb];
   if (p.leftpad_k) { k_off = p.leftpad_k[bidb]; sk_b -= k_off; }  // seqlen_k = seqused_k - leftpad_k (block_info.h:12-45)
   const int rows_total = sq_b * p.gp;
   const int row0 = m_block * 256;

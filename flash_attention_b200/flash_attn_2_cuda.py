@@ -21,6 +21,7 @@ import torch
 from . import _lib
 
 _DT = {torch.float16: _lib.FP16, torch.bfloat16: _lib.BF16}
+_PACK = {None: 0, True: 1, False: 2}  # FA3 `pack_gqa` -> fa_b200_fwd_args.pack_gqa
 
 
 def _check(cond: bool, msg: str):
@@ -123,7 +124,7 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
 
 # --------------------------------------------------------------------------------------- fwd_fp8
 def fwd_fp8(q, k, v, out_, q_descale, k_descale, v_descale, softmax_scale, is_causal, window_size_left,
-            window_size_right, softcap=0.0, alibi_slopes_=None, num_splits=0) -> List[torch.Tensor]:
+            window_size_right, softcap=0.0, alibi_slopes_=None, num_splits=0, pack_gqa=None) -> List[torch.Tensor]:
     """FP8 e4m3 forward (no FA2 equivalent: flash_api.cpp:396 rejects fp8; spec = FA3 `mha_fwd` descale
     arguments, hopper/flash_api.cpp, and flash_attn/cute/interface.py:637-643).  q/k/v torch.float8_e4m3fn,
     descales (b, h_k) fp32 or None (= 1.0); output bf16 -> [out, softmax_lse(b,h,sq)]."""
@@ -164,6 +165,7 @@ def fwd_fp8(q, k, v, out_, q_descale, k_descale, v_descale, softmax_scale, is_ca
     a.softmax_scale, a.softcap = softmax_scale, softcap
     a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
     a.num_splits = num_splits
+    a.pack_gqa = _PACK[pack_gqa]
     _alibi(a, alibi_slopes_, b, h)
     with torch.cuda.device(q.device):
         ws = _workspace(lib, a, q.device)  # noqa: F841
@@ -171,10 +173,54 @@ def fwd_fp8(q, k, v, out_, q_descale, k_descale, v_descale, softmax_scale, is_ca
     return [out, lse]
 
 
+def fwd_ex(q, k, v, softmax_scale, is_causal, window_size_left, window_size_right, softcap=0.0, num_splits=0,
+           pack_gqa=None, alibi_slopes_=None) -> List[torch.Tensor]:
+    """Dense forward with the FA3 scheduling knobs (`num_splits`, `pack_gqa`; hopper/flash_api.cpp mha_fwd) -> [out, lse]."""
+    lib = _lib.load()
+    _common_checks(q, k, v)
+    b, sq, h, d = q.shape
+    sk, hk = k.shape[1], k.shape[2]
+    _check(d % 8 == 0 and h % hk == 0, "bad head_size / number of heads")
+    out = torch.empty_like(q)
+    lse = torch.empty((b, h, sq), dtype=torch.float32, device=q.device)
+    a = _lib.FwdArgs()
+    a.q, a.k, a.v, a.out, a.softmax_lse = _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse)
+    a.q_batch_stride, a.q_row_stride, a.q_head_stride = q.stride(0), q.stride(1), q.stride(2)
+    a.k_batch_stride, a.k_row_stride, a.k_head_stride = k.stride(0), k.stride(1), k.stride(2)
+    a.v_batch_stride, a.v_row_stride, a.v_head_stride = v.stride(0), v.stride(1), v.stride(2)
+    a.o_batch_stride, a.o_row_stride, a.o_head_stride = out.stride(0), out.stride(1), out.stride(2)
+    a.b, a.seqlen_q, a.seqlen_k, a.h, a.h_k, a.d = b, sq, sk, h, hk, d
+    a.dtype = _DT[q.dtype]
+    a.softmax_scale, a.softcap = softmax_scale, softcap
+    a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
+    a.num_splits, a.pack_gqa = num_splits, _PACK[pack_gqa]
+    _alibi(a, alibi_slopes_, b, h)
+    with torch.cuda.device(q.device):
+        ws = _workspace(lib, a, q.device)  # noqa: F841
+        _lib.check(lib.fa_b200_mha_fwd(C.byref(a), _stream(q)))
+    return [out, lse]
+
+
+def plan_kvcache(batch, seqlen_q, seqlen_k, h, hk, d, page_size, causal, wl, wr, num_splits=0, pack_gqa=None):
+    """Host-only: (num_splits, gqa_pack_factor, num_m_blocks) the library will use for this decode shape."""
+    lib = _lib.load()
+    a = _lib.FwdArgs()
+    a.b, a.seqlen_q, a.seqlen_k, a.h, a.h_k, a.d = batch, seqlen_q, seqlen_k, h, hk, d
+    a.dtype = _lib.BF16
+    a.seqused_k = C.c_void_p(16)  # non-null marks the kvcache mode for the planner; never dereferenced on the host
+    a.is_causal, a.window_size_left, a.window_size_right = int(causal), wl, wr
+    a.num_splits, a.pack_gqa = num_splits, _PACK[pack_gqa]
+    if page_size:
+        a.block_table, a.page_block_size, a.num_pages = C.c_void_p(16), page_size, 1
+    out = (C.c_int32 * 3)()
+    _lib.check(lib.fa_b200_fwd_plan(C.byref(a), out))
+    return int(out[0]), int(out[1]), int(out[2])
+
+
 # --------------------------------------------------------------------------------------- varlen_fwd
 def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_, block_table_, alibi_slopes_,
                max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal, window_size_left,
-               window_size_right, softcap, return_softmax, gen_=None, num_splits=0) -> List[torch.Tensor]:
+               window_size_right, softcap, return_softmax, gen_=None, num_splits=0, seqused_q=None) -> List[torch.Tensor]:
     """mha_varlen_fwd (flash_api.cpp:538-788).  q (total_q,h,d); k/v (total_k,h_k,d) or paged
     (num_blocks,page,h_k,d) with block_table (b,max_blocks) -> [out, softmax_lse(h,total_q), p, rng_state]."""
     lib = _lib.load()
@@ -242,6 +288,9 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_,
     if seqused_k is not None:
         _check(seqused_k.dtype == torch.int32 and seqused_k.is_cuda and seqused_k.is_contiguous(), "seqused_k must be int32 contiguous cuda")
         a.seqused_k = _ptr(seqused_k)
+    if seqused_q is not None:
+        _check(seqused_q.dtype == torch.int32 and seqused_q.is_cuda and seqused_q.is_contiguous(), "seqused_q must be int32 contiguous cuda")
+        a.seqused_q = _ptr(seqused_q)
     a.softmax_scale, a.softcap = softmax_scale, softcap
     a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
     a.num_splits = 1

@@ -66,6 +66,7 @@ typedef struct fa_b200_fwd_args {
   const int32_t* cu_seqlens_q; /* (b+1) or NULL */
   const int32_t* cu_seqlens_k; /* (b+1) or NULL */
   const int32_t* seqused_k;    /* (b) or NULL: number of valid keys per batch (cache_seqlens) */
+  const int32_t* seqused_q;    /* (b) or NULL: number of valid queries per batch (FA3 `seqused_q`); rows beyond are not written */
   const int32_t* cache_batch_idx; /* (b) or NULL: batch b reads cache row cache_batch_idx[b] (kvcache, not paged) */
   const int32_t* leftpad_k;    /* (b) or NULL: keys of batch b start at row leftpad_k[b] (kvcache, not paged) */
   const int32_t* block_table;  /* (b, max_blocks_per_seq) or NULL */
@@ -84,6 +85,7 @@ typedef struct fa_b200_fwd_args {
   int64_t q_descale_batch_stride, k_descale_batch_stride, v_descale_batch_stride;
   /* split-KV */
   int32_t num_splits;          /* 0 = heuristic, 1 = never split, >1 = forced */
+  int32_t pack_gqa;            /* 0 = heuristic, 1 = pack the query heads of a KV head into M, 2 = never (FA3 `pack_gqa`) */
   void* workspace; size_t workspace_bytes;
   /* debugging: optional fp32 buffer (128x128) receiving the raw S tile of CTA (0,0,0) */
   float* debug_s;
@@ -121,6 +123,8 @@ int fa_b200_mha_fwd_kvcache(const fa_b200_fwd_args* args, fa_b200_stream_t strea
 size_t fa_b200_fwd_workspace_bytes(const fa_b200_fwd_args* args);
 /* the split count the call will use (after heuristic / clamping) */
 int fa_b200_fwd_num_splits(const fa_b200_fwd_args* args);
+/* the full plan: out[0] = num_splits, out[1] = GQA pack factor, out[2] = number of 256-row m-blocks (FA3 get_scheduler_metadata) */
+int fa_b200_fwd_plan(const fa_b200_fwd_args* args, int32_t out[3]);
 
 /* ---- backward ---- */
 int fa_b200_mha_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream);
