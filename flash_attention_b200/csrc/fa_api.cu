@@ -113,6 +113,7 @@ int splits_heuristic(int ctas, int sms, int n_blocks, int max_splits) {
 enum FwdMode { kDense = 0, kVarlen = 1, kKvcache = 2 };
 
 struct FwdPlan {
+  int tiles;     // query tiles per CTA: 2 = throughput config (1 CTA/SM), 1 = latency config (2 CTAs/SM)
   int kD;        // padded head dim of the kernel (64 or 128)
   int gp;        // packed heads
   int num_m_blocks;
@@ -153,21 +154,35 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   pl->has_right = wr >= 0;
   pl->wl = wl;
   pl->wr = wr;
-  // GQA head packing: fold the g query heads of one KV head into the M dimension when a tile of
-  // 256 query positions would otherwise be mostly empty (decode / short queries).
+  // Tile configuration: short work items (decode, few K/V blocks per CTA) take the 1-tile kernel, of which two
+  // CTAs fit on an SM and overlap each other's prologue / softmax / epilogue; long streams take the 2-tile kernel
+  // (half the K/V shared-memory traffic per query row).  FA_B200_FWD_TILES=1|2 overrides (experiments).
   const int g = a.h / a.h_k;
+  {
+    int est_blocks = cdiv(a.seqlen_k, 128);
+    if (pl->has_right && !pl->has_left && a.seqlen_q == a.seqlen_k) est_blocks = (est_blocks + 1) / 2;
+    if (pl->has_left) est_blocks = std::min(est_blocks, cdiv(wl + std::max(wr, 0) + 256, 128));
+    // measured (profiles/r01_v3_sweep_tiles.txt): causal forward is faster with 1-tile CTAs up to s = 16k
+    // (est_blocks <= 64), non-causal only up to s = 1k (est_blocks <= 8)
+    const int limit = pl->has_right ? 64 : 8;
+    pl->tiles = (a.seqlen_q * (g > 1 && is_pow2(g) ? g : 1) <= 128 || est_blocks <= limit) ? 1 : 2;
+    if (const char* e = getenv("FA_B200_FWD_TILES")) { if (e[0] == '1') pl->tiles = 1; if (e[0] == '2') pl->tiles = 2; }
+  }
+  const int rows_cta = 128 * pl->tiles;
+  // GQA head packing: fold the g query heads of one KV head into the M dimension when a CTA's worth of query
+  // positions would otherwise be mostly empty (decode / short queries).
   int gp = 1;
   if (a.pack_gqa == 1 && g > 1) {
     if (!is_pow2(g) || g > 128) return set_error("pack_gqa needs a power-of-two group size <= 128");
     gp = g;
   } else if (a.pack_gqa == 0 && g > 1 && is_pow2(g) && g <= 128) {
     const int sq = a.seqlen_q;
-    const double eff_unpacked = double(sq) / (cdiv(sq, 256) * 256);
-    const double eff_packed = double(sq) * g / (cdiv(sq * g, 256) * 256);
+    const double eff_unpacked = double(sq) / (cdiv(sq, rows_cta) * rows_cta);
+    const double eff_packed = double(sq) * g / (cdiv(sq * g, rows_cta) * rows_cta);
     if (eff_packed > 1.2 * eff_unpacked) gp = g;
   }
   pl->gp = gp;
-  pl->num_m_blocks = cdiv(a.seqlen_q * gp, 256);
+  pl->num_m_blocks = cdiv(a.seqlen_q * gp, rows_cta);
   // split-KV (flash_api.cpp:317-347): heuristic when num_splits == 0; never for packed-varlen q
   int splits = a.num_splits;
   if (splits < 0) return set_error("num_splits must be non-negative");
@@ -177,13 +192,14 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   } else if (splits == 0) {
     const int n_blocks = cdiv(a.seqlen_k, 128);
     const int ctas = pl->num_m_blocks * (a.h / gp) * a.b;
-    splits = splits_heuristic(ctas, num_sms(), n_blocks, 128);
+    const int slots = num_sms() * (pl->tiles == 1 ? 2 : 1);  // resident CTAs per wave
+    splits = splits_heuristic(ctas, slots, n_blocks, 128);
     // B200 refinement for long-KV decode: the reference rule returns 1 as soon as the grid covers 80 % of the
     // SMs, but e.g. 256 CTAs on 148 SMs run 2 waves at 86 % occupancy.  When every split still streams >= 32
     // blocks (partials + combine are then noise) take the smallest split count that lifts wave efficiency by
     // > 5 % (C5: 1 -> 4 splits, 5662 -> 6132 GB/s measured).
     if (splits == 1 && mode == kKvcache && n_blocks >= 64) {
-      auto eff = [&](int s) { float w = float(ctas) * s / num_sms(); return w / std::ceil(w); };
+      auto eff = [&](int s) { float w = float(ctas) * s / slots; return w / std::ceil(w); };
       float best = eff(1);
       for (int s = 2; s <= 8 && n_blocks / s >= 32; ++s)
         if (eff(s) > best * 1.05f) { best = eff(s); splits = s; }
@@ -200,11 +216,11 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   return 0;
 }
 
-template <typename T, int kD>
-static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
-  using Cfg = FwdCfg<kD, EltInfo<T>::kBytes>;
+template <typename T, int kD, int kTiles>
+static int launch_fwd_kernel_t(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+  using Cfg = FwdCfg<kD, EltInfo<T>::kBytes, kTiles>;
   static bool configured = false;
-  auto kern = fa_fwd_kernel<T, kD>;
+  auto kern = fa_fwd_kernel<T, kD, kTiles>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(fwd): ") + cudaGetErrorString(e));
@@ -215,6 +231,11 @@ static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("fa_fwd_kernel launch: ") + cudaGetErrorString(e));
   return 0;
+}
+
+template <typename T, int kD>
+static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream, int tiles) {
+  return tiles == 1 ? launch_fwd_kernel_t<T, kD, 1>(kp, grid, stream) : launch_fwd_kernel_t<T, kD, 2>(kp, grid, stream);
 }
 
 static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream) {
@@ -300,12 +321,12 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   dim3 grid(pl.num_m_blocks, a.h / gp, a.b * pl.num_splits);
   int rc;
   if (fp8) {
-    rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream);
+    rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream, pl.tiles);
   } else if (a.dtype == FA_B200_BF16) {
-    rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream)
-                     : launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream);
+    rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream, pl.tiles)
+                     : launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream, pl.tiles);
   } else {
-    rc = pl.kD == 64 ? launch_fwd_kernel<__half, 64>(kp, grid, stream) : launch_fwd_kernel<__half, 128>(kp, grid, stream);
+    rc = pl.kD == 64 ? launch_fwd_kernel<__half, 64>(kp, grid, stream, pl.tiles) : launch_fwd_kernel<__half, 128>(kp, grid, stream, pl.tiles);
   }
   if (rc) return rc;
   if (pl.num_splits > 1) {

@@ -63,25 +63,34 @@ struct FwdKernelParams {
   float softcap_pre;        // softmax_scale / softcap, 0 = off
 };
 
-template <int kD, int kBytes = 2>
+// kTiles = 2: the throughput configuration (256 query rows per CTA, 5-stage K/V ring, one CTA per SM).
+// kTiles = 1: the latency configuration for short work items (decode, short / causal sequences): 128 rows per CTA,
+//             2-stage ring, 256 TMEM columns, 256 threads -> TWO CTAs per SM, which overlap each other's softmax /
+//             MMA phases and hide each other's prologue and epilogue.
+template <int kD, int kBytes = 2, int kTiles = 2>
 struct FwdCfg {
   static constexpr int kBlockM = 128;
   static constexpr int kBlockN = 128;
-  static constexpr int kStages = 5;
-  static constexpr int kThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle}
+  static constexpr int kStages = kTiles == 2 ? 5 : 2;
+  static constexpr int kThreads = 128 * (kTiles + 1);  // softmax warpgroup per tile + {MMA, TMA, tail cleaner, idle}
+  static constexpr int kCtasPerSm = kTiles == 2 ? 1 : 2;
+  static constexpr int kTmemCols = 256 * kTiles;
+  static constexpr int kWarpMma = 4 * kTiles, kWarpTma = 4 * kTiles + 1, kWarpClean = 4 * kTiles + 2;
   // setmaxnreg split: the CTA's register pool is kThreads * 168 (launch bounds 384 x 1 -> 168 regs/thread);
   // 2 softmax warpgroups + 1 MMA/TMA warpgroup must not ask for more than that or setmaxnreg.inc blocks forever.
-  static constexpr int kRegsSoftmax = 216;
-  static constexpr int kRegsOther = 72;
-  static_assert(2 * kRegsSoftmax + kRegsOther <= 3 * 168, "setmaxnreg split exceeds the CTA register pool");
+  static constexpr int kRegsSoftmax = kTiles == 2 ? 216 : 200;
+  static constexpr int kRegsOther = kTiles == 2 ? 72 : 56;
+  static_assert(kTiles * kRegsSoftmax + kRegsOther <= (kTiles + 1) * (kTiles == 2 ? 168 : 128),
+                "setmaxnreg split exceeds the CTA register pool");
   static constexpr int kPanels = kD * kBytes / 128;        // 128-byte swizzle panels per row (64 x 16-bit or 128 x 8-bit)
   static constexpr int kPanelElems = 128 / kBytes;
   static constexpr int kPanelBytes = 128 * 128;           // 128 rows x 128 B
   static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
-  static constexpr int kSmemQ = 2 * kTileBytes;
+  static constexpr int kSmemQ = kTiles * kTileBytes;
   static constexpr int kSmemKV = kStages * kTileBytes;
   static constexpr int kNumBars = 2 + 2 * kStages + 9;
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
+  static_assert(kSmemBytes * kCtasPerSm <= 232448, "shared memory budget");
 };
 
 // 16-bit element traits
@@ -110,13 +119,14 @@ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; 
 #define FA_FWD_POLY_PAIRS 1  // measured on B200 (r01): 0 -> 1315, 1 -> 1339, 2 -> 1307, 3 -> 1147, 4 -> 1046 TFLOP/s fwd
 #endif
 
-template <typename T, int kD>
-__global__ void __launch_bounds__(FwdCfg<kD>::kThreads, 1)
+template <typename T, int kD, int kTiles>
+__global__ void __launch_bounds__((FwdCfg<kD, 2, kTiles>::kThreads), (FwdCfg<kD, 2, kTiles>::kCtasPerSm))
 fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   constexpr int kBytes = EltInfo<T>::kBytes;
   constexpr bool kFp8 = EltInfo<T>::kFp8;
   using OutT = typename EltInfo<T>::Out;
-  using Cfg = FwdCfg<kD, kBytes>;
+  using Cfg = FwdCfg<kD, kBytes, kTiles>;
+  constexpr int kRowsPerCta = 128 * kTiles;
   constexpr int S = Cfg::kStages;
   constexpr float kNegInf = -INFINITY;
   constexpr int kPolyPairs = FA_FWD_POLY_PAIRS;  // of every 4 element pairs, how many use the FMA-pipe exp2
@@ -135,9 +145,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   if (p.seqused_q) sq_b = p.seqused_q[bidb];
   if (p.leftpad_k) { k_off = p.leftpad_k[bidb]; sk_b -= k_off; }  // seqlen_k = seqused_k - leftpad_k (block_info.h:12-45)
   const int rows_total = sq_b * p.gp;
-  const int row0 = m_block * 256;
+  const int row0 = m_block * kRowsPerCta;
   if (row0 >= rows_total) return;  // uniform for the whole CTA, nothing allocated yet
-  const int ntiles = (row0 + 128 < rows_total) ? 2 : 1;
+  const int ntiles = (kTiles == 2 && row0 + 128 < rows_total) ? 2 : 1;
 
   const int hk_idx = (slot * p.gp) / p.g;
   const int shift = sk_b - sq_b;  // bottom-right alignment (mask.h:172-173)
@@ -145,7 +155,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   int n_min = 0, n_max = nblk_total;
   {
     const int qpos_lo = row0 / p.gp;
-    int last_row = row0 + 255 < rows_total - 1 ? row0 + 255 : rows_total - 1;
+    int last_row = row0 + kRowsPerCta - 1 < rows_total - 1 ? row0 + kRowsPerCta - 1 : rows_total - 1;
     const int qpos_hi = last_row / p.gp;
     if (p.has_right) {
       int lim = qpos_hi + 1 + shift + p.wr;  // exclusive column limit of the last row
@@ -189,12 +199,12 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 9 && lane == 0) {
+  if (warp == Cfg::kWarpTma && lane == 0) {
     tma_prefetch_desc(&p.tm_q);
     tma_prefetch_desc(&p.tm_k);
     tma_prefetch_desc(&p.tm_v);
   }
-  if (warp == 8) {
+  if (warp == Cfg::kWarpMma) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_q_full(i), 1);
@@ -211,7 +221,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(sTmemPtr, 512);
+    tmem_alloc(sTmemPtr, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -220,10 +230,10 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   // register re-distribution (per warpgroup): softmax rows live in registers, the MMA/TMA warps need few
-  if (warp >= 8) {
+  if (warp >= Cfg::kWarpMma) {
   reg_dealloc<Cfg::kRegsOther>();
   // ================================================================== TMA producer
-  if (warp == 9) {
+  if (warp == Cfg::kWarpTma) {
     if (nblocks > 0 && elect_one()) {
       const int bq = p.cu_seqlens_q ? 0 : bidb;
       for (int i = 0; i < ntiles; ++i) {
@@ -260,7 +270,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
     __syncwarp();
   }
   // ================================================================== MMA issuer (one elected thread)
-  else if (warp == 8) {
+  else if (warp == Cfg::kWarpMma) {
     if (nblocks > 0 && elect_one()) {
       constexpr uint32_t fmt = Elt<T>::kFmt;
       constexpr uint32_t idesc_qk = make_idesc(fmt, fmt, 0, 0, 128, 128);
@@ -272,7 +282,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       auto lo_of = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
       auto mk = [](uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; };
       const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
-      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+      const uint32_t tO[2] = {tmem_base + kTiles * 128, tmem_base + kTiles * 128 + 128};
 
       auto issue_qk = [&](int i, int slot_k) {
         const uint32_t la = lo_of(sQ + i * Cfg::kTileBytes) | uint32_t(desc_k_major);
@@ -334,7 +344,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
     __syncwarp();
   }
   // ================================================================== V-tail cleaner (otherwise idle warp)
-  else if (warp == 10) {
+  else if (warp == Cfg::kWarpClean) {
     if (nblocks > 0 && v_tail) {
       // Rows of the last V block beyond seqlen_k may hold garbage (kv-cache tail, next sequence): P is
       // exactly 0 there but 0 * NaN would poison O, so clear them before the first PV
@@ -360,7 +370,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       const int wq = warp & 3;
       const uint32_t lane_sel = uint32_t(wq * 32) << 16;
       const uint32_t tS = tmem_base + lane_sel + tile * 128;
-      const uint32_t tO = tmem_base + lane_sel + 256 + tile * 128;
+      const uint32_t tO = tmem_base + lane_sel + kTiles * 128 + tile * 128;
       const int r = row0 + tile * 128 + wq * 32 + lane;  // packed row of this thread
       const int qpos = r / p.gp;
       const int head = slot * p.gp + (r - qpos * p.gp);
@@ -619,9 +629,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == Cfg::kWarpMma) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

@@ -246,9 +246,11 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 }
 // 2^x for a pair on the FMA pipe (no MUFU): round-to-nearest range reduction x = n + f, f in [-0.5, 0.5],
 // 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5, far below the 16-bit rounding of P), 2^n by
-// adding n to the exponent field.  Inputs must be <= ~120; values below -125 are clamped (result ~ 1e-38, i.e. 0 after 16-bit rounding).
+// adding n to the exponent field.  Inputs must be <= ~120; inputs below -125 (incl. -inf of masked scores) give
+// exactly 0 -- a fully masked row must keep a row sum of exactly 0.
 __device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& r1) {
   const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it rounds to an integer kept in the low mantissa bits
+  const bool z0 = x0 < -125.0f, z1 = x1 < -125.0f;
   x0 = fmaxf(x0, -125.0f);
   x1 = fmaxf(x1, -125.0f);
   const uint64_t x = pack2(x0, x1);
@@ -261,8 +263,8 @@ __device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& 
   float t0, t1, p0, p1;
   unpack2(t, t0, t1);
   unpack2(pl, p0, p1);
-  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  r0 = z0 ? 0.f : __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = z1 ? 0.f : __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 // {lo, hi} -> packed 16-bit pair (lo in bits [0,16))

@@ -100,3 +100,13 @@ def test_full_size_rows_vs_oracle(fab):
         bi, hi = 3, 11
         check_fwd(out[bi:bi + 1, -256:, hi:hi + 1], lse[bi:bi + 1, hi:hi + 1, -256:], q[bi:bi + 1, -256:, hi:hi + 1],
                   k[bi:bi + 1, :, hi:hi + 1], v[bi:bi + 1, :, hi:hi + 1], causal=causal)
+
+
+def test_dead_and_live_rows_in_one_tile(fab):
+    """sq > sk, causal: rows 0..sq-sk-1 see no key.  When dead and live rows share a 128-row tile the dead rows
+    must still come out as exact zeros with lse = +inf (regression: the polynomial exp2 returned 2^-125 instead of 0
+    for -inf scores, which gave fully masked rows a non-zero row sum)."""
+    q, k, v = make_qkv(1, 256, 100, 2, 2, 128)
+    out, lse, _ = fab.flash_attn_func(q, k, v, causal=True, return_attn_probs=True)
+    assert torch.all(out[:, :156] == 0) and torch.all(torch.isinf(lse[:, :, :156]))
+    check_fwd(out, lse, q, k, v, causal=True)
