@@ -128,7 +128,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   if (a.b <= 0) return set_error("batch size must be positive");
   if (a.d <= 0 || a.d > 256) return set_error("FlashAttention forward only supports head dimension at most 256");
   if (a.d % 8 != 0) return set_error("head_size should be a multiple of 8");
-  if (a.d > 128) return set_error("this build of fa_b200 supports head dimension at most 128");
+  if (a.d > 128 && a.dtype == FA_B200_FP8_E4M3) return set_error("fp8 forward supports head dimension at most 128");
   if (a.h <= 0 || a.h_k <= 0 || a.h % a.h_k != 0)
     return set_error("Number of heads in key/value must divide number of heads in query");
   if (a.softcap < 0.f) return set_error("softcap must be non-negative");
@@ -141,7 +141,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
       return set_error("Paged KV cache block size must be divisible by 128");
     if (a.num_pages <= 0) return set_error("num_pages must be positive for a paged KV cache");
   }
-  pl->kD = (a.d <= 64 && a.dtype != FA_B200_FP8_E4M3) ? 64 : 128;  // fp8 rows are always one 128-byte panel
+  pl->kD = a.d > 128 ? 256 : ((a.d <= 64 && a.dtype != FA_B200_FP8_E4M3) ? 64 : 128);  // fp8 rows: one 128-byte panel
   if (a.dtype == FA_B200_FP8_E4M3 && a.d % 16 != 0) return set_error("fp8 head_size should be a multiple of 16");
   // window canonicalisation (flash_api.cpp:414-419, set_params_fprop :150-164)
   int wl = a.window_size_left, wr = a.window_size_right;
@@ -167,6 +167,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     const int limit = pl->has_right ? 64 : 8;
     pl->tiles = (a.seqlen_q * (g > 1 && is_pow2(g) ? g : 1) <= 128 || est_blocks <= limit) ? 1 : 2;
     if (const char* e = getenv("FA_B200_FWD_TILES")) { if (e[0] == '1') pl->tiles = 1; if (e[0] == '2') pl->tiles = 2; }
+    if (pl->kD == 256) pl->tiles = 1;  // S (128) + O (256) TMEM columns: one tile per CTA (forward only)
   }
   const int rows_cta = 128 * pl->tiles;
   // GQA head packing: fold the g query heads of one KV head into the M dimension when a CTA's worth of query
@@ -324,9 +325,12 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream, pl.tiles);
   } else if (a.dtype == FA_B200_BF16) {
     rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream, pl.tiles)
-                     : launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream, pl.tiles);
+       : pl.kD == 128 ? launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream, pl.tiles)
+                      : launch_fwd_kernel_t<__nv_bfloat16, 256, 1>(kp, grid, stream);
   } else {
-    rc = pl.kD == 64 ? launch_fwd_kernel<__half, 64>(kp, grid, stream, pl.tiles) : launch_fwd_kernel<__half, 128>(kp, grid, stream, pl.tiles);
+    rc = pl.kD == 64 ? launch_fwd_kernel<__half, 64>(kp, grid, stream, pl.tiles)
+       : pl.kD == 128 ? launch_fwd_kernel<__half, 128>(kp, grid, stream, pl.tiles)
+                      : launch_fwd_kernel_t<__half, 256, 1>(kp, grid, stream);
   }
   if (rc) return rc;
   if (pl.num_splits > 1) {

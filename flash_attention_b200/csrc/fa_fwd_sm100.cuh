@@ -74,7 +74,7 @@ struct FwdCfg {
   static constexpr int kStages = kTiles == 2 ? 5 : 2;
   static constexpr int kThreads = 128 * (kTiles + 1);  // softmax warpgroup per tile + {MMA, TMA, tail cleaner, idle}
   static constexpr int kCtasPerSm = kTiles == 2 ? 1 : 2;
-  static constexpr int kTmemCols = 256 * kTiles;
+  static constexpr int kTmemCols = (kTiles * (128 + kD) <= 256) ? 256 : 512;  // S (128) + O (kD) per tile, power of two
   static constexpr int kWarpMma = 4 * kTiles, kWarpTma = 4 * kTiles + 1, kWarpClean = 4 * kTiles + 2;
   // setmaxnreg split: the CTA's register pool is kThreads * 168 (launch bounds 384 x 1 -> 168 regs/thread);
   // 2 softmax warpgroups + 1 MMA/TMA warpgroup must not ask for more than that or setmaxnreg.inc blocks forever.
@@ -90,7 +90,7 @@ struct FwdCfg {
   static constexpr int kSmemKV = kStages * kTileBytes;
   static constexpr int kNumBars = 2 + 2 * kStages + 9;
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
-  static_assert(kSmemBytes * kCtasPerSm <= 232448, "shared memory budget");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");  // hd256 (1 tile, 194 KB) runs one CTA per SM
 };
 
 // 16-bit element traits
@@ -282,7 +282,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       auto lo_of = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
       auto mk = [](uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; };
       const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
-      const uint32_t tO[2] = {tmem_base + kTiles * 128, tmem_base + kTiles * 128 + 128};
+      const uint32_t tO[2] = {tmem_base + kTiles * 128, tmem_base + kTiles * 128 + kD};
 
       auto issue_qk = [&](int i, int slot_k) {
         const uint32_t la = lo_of(sQ + i * Cfg::kTileBytes) | uint32_t(desc_k_major);
@@ -370,7 +370,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       const int wq = warp & 3;
       const uint32_t lane_sel = uint32_t(wq * 32) << 16;
       const uint32_t tS = tmem_base + lane_sel + tile * 128;
-      const uint32_t tO = tmem_base + lane_sel + kTiles * 128 + tile * 128;
+      const uint32_t tO = tmem_base + lane_sel + kTiles * 128 + tile * kD;
       const int r = row0 + tile * 128 + wq * 32 + lane;  // packed row of this thread
       const int qpos = r / p.gp;
       const int head = slot * p.gp + (r - qpos * p.gp);

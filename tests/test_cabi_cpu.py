@@ -75,3 +75,24 @@ def test_argument_errors_are_reported_without_gpu(fa_lib):
     assert fa_lib.fa_b200_mha_fwd(C.byref(a), None) != 0
     assert b"multiple of 8" in fa_lib.fa_b200_last_error()
     assert fa_lib.fa_b200_mha_fwd(None, None) != 0
+
+
+def test_forward_plan_host_logic(fa_lib):
+    """Host-only planning (no GPU): GQA packing, split-KV and the 1-tile / 2-tile choice for the BASELINE shapes."""
+    from flash_attention_b200 import flash_attn_2_cuda as op
+
+    # C5 decode: b64 sq1 h32/4 kv65536 paged(256): 8 query heads packed into M, one 128-row CTA per (b, kv head),
+    # split so that 2 CTAs x 148 SMs stay busy
+    splits, gp, mblocks = op.plan_kvcache(64, 1, 65536, 32, 4, 128, 256, False, -1, -1)
+    assert gp == 8 and mblocks == 1 and 1 <= splits <= 8
+    # forced knobs
+    assert op.plan_kvcache(64, 1, 65536, 32, 4, 128, 256, False, -1, -1, num_splits=3)[0] == 3
+    assert op.plan_kvcache(64, 1, 65536, 32, 4, 128, 256, False, -1, -1, pack_gqa=False)[1] == 1
+    # long prefill against a cache: no packing, 256-row CTAs (2-tile kernel) for the non-causal stream
+    splits, gp, mblocks = op.plan_kvcache(4, 8192, 8192, 16, 16, 128, 0, False, -1, -1)
+    assert (splits, gp, mblocks) == (1, 1, 8192 // 256)
+    # causal at the same size takes the 1-tile kernel (measured faster up to 16k): 128-row CTAs
+    assert op.plan_kvcache(4, 8192, 8192, 16, 16, 128, 0, True, -1, -1)[2] == 8192 // 128
+    # few CTAs and a long KV: split heuristic kicks in (flash_api.cpp:281-315 rule on 2 x 148 CTA slots)
+    splits, gp, mblocks = op.plan_kvcache(1, 1, 16384, 8, 8, 128, 0, False, -1, -1)
+    assert splits > 1

@@ -110,3 +110,49 @@ def test_dead_and_live_rows_in_one_tile(fab):
     out, lse, _ = fab.flash_attn_func(q, k, v, causal=True, return_attn_probs=True)
     assert torch.all(out[:, :156] == 0) and torch.all(torch.isinf(lse[:, :, :156]))
     check_fwd(out, lse, q, k, v, causal=True)
+
+
+@pytest.mark.parametrize("d", [160, 192, 224, 256])
+@pytest.mark.parametrize("causal", [False, True])
+def test_forward_head_dims_up_to_256(fab, d, causal):
+    """head dims 129..256 run the 1-tile forward configuration (S 128 + O 256 TMEM columns); forward only."""
+    q, k, v = make_qkv(2, 300, 421, 4, 2, d)
+    out, lse, _ = fab.flash_attn_func(q, k, v, causal=causal, return_attn_probs=True)
+    check_fwd(out, lse, q, k, v, causal=causal)
+
+
+def test_backward_head_dim_above_128_is_rejected(fab):
+    q, k, v = make_qkv(1, 128, 128, 2, 2, 256)
+    q.requires_grad_(True)
+    out = fab.flash_attn_func(q, k, v)
+    with pytest.raises(RuntimeError, match="at most 128"):
+        out.backward(torch.randn_like(out))
+
+
+def test_forward_is_bitwise_reproducible(fab):
+    """Reference: test_flash_attn_race_condition (tests/test_flash_attn.py:2199): repeated runs must be bit-equal."""
+    q, k, v = make_qkv(8, 500, 777, 6, 2, 128)
+    o0, l0, _ = fab.flash_attn_func(q, k, v, causal=True, return_attn_probs=True)
+    for _ in range(50):
+        o, l, _ = fab.flash_attn_func(q, k, v, causal=True, return_attn_probs=True)
+        assert torch.equal(o, o0) and torch.equal(l, l0)
+
+
+def test_varlen_with_empty_sequences(fab):
+    """cu_seqlens with zero-length query and key sequences (reference varlen tests draw random lengths incl. 0)."""
+    from oracle.attention_oracle import attention_oracle_varlen
+
+    h, hk, d = 4, 2, 128
+    lens_q, lens_k = [0, 130, 64, 5], [77, 0, 200, 5]
+    cu_q = torch.tensor([0, 0, 130, 194, 199], dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor([0, 77, 77, 277, 282], dtype=torch.int32, device="cuda")
+    q = torch.randn(199, h, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    k = torch.randn(282, hk, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    v = torch.randn(282, hk, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    out, lse, _ = fab.flash_attn_varlen_func(q, k, v, cu_q, cu_k, 130, 200, causal=False, return_attn_probs=True)
+    ref, lse_ref = attention_oracle_varlen(q.detach().cpu(), k.detach().cpu(), v.detach().cpu(), cu_q.cpu(), cu_k.cpu(), 130, 200)
+    assert (out.float().cpu() - ref.float()).abs().max().item() <= 2e-2
+    assert torch.all(out[0:130] == 0) and torch.all(torch.isinf(lse[:, 0:130]))  # sequence 1 has no keys
+    out.backward(torch.randn_like(out))
+    assert torch.isfinite(q.grad).all() and torch.isfinite(k.grad).all() and torch.isfinite(v.grad).all()
+    assert torch.all(q.grad[0:130] == 0) and torch.all(k.grad[0:77] == 0)  # no partner -> zero gradient
