@@ -100,10 +100,12 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   if (int rc = map16(&kp.tm_k, a.k, a.k_batch_stride, a.k_row_stride, a.k_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
   if (int rc = map16(&kp.tm_v, a.v, a.v_batch_stride, a.v_row_stride, a.v_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
   {
+    constexpr uint64_t esz = FA_BWD_DQ_FP16 ? 2 : 4;
     uint64_t dims[4] = {uint64_t(kD), uint64_t(sq_r), uint64_t(a.h), uint64_t(a.b)};
-    uint64_t str[3] = {uint64_t(kD) * 4, uint64_t(sq_r) * kD * 4, uint64_t(a.h) * sq_r * kD * 4};
-    uint32_t box[4] = {32, 128, 1, 1};
-    if (int rc = make_tmap(&kp.tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, dims, str, box)) return rc;
+    uint64_t str[3] = {uint64_t(kD) * esz, uint64_t(sq_r) * kD * esz, uint64_t(a.h) * sq_r * kD * esz};
+    uint32_t box[4] = {uint32_t(128 / esz), 128, 1, 1};
+    if (int rc = make_tmap(&kp.tm_dq, FA_BWD_DQ_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                           dq_accum, dims, str, box)) return rc;
   }
   kp.lse_log2 = lse_log2;
   kp.dq_semaphore = a.deterministic ? reinterpret_cast<int*>(ws + pl.off_sem) : nullptr;
