@@ -42,6 +42,8 @@ class FwdArgs(C.Structure):
         ("num_splits", _i32), ("pack_gqa", _i32),
         ("workspace", _vp), ("workspace_bytes", _sz),
         ("debug_s", _vp),
+        ("p_dropout", C.c_float), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+        ("s_dmask", _vp),
     ]
 
 
@@ -68,6 +70,8 @@ class BwdArgs(C.Structure):
         ("is_causal", _i32), ("window_size_left", _i32), ("window_size_right", _i32),
         ("deterministic", _i32),
         ("workspace", _vp), ("workspace_bytes", _sz),
+        ("p_dropout", C.c_float), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+        ("rng_state", _vp),
     ]
 
 

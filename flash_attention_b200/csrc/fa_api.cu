@@ -119,6 +119,7 @@ struct FwdPlan {
   int num_m_blocks;
   int num_splits;
   int has_left, has_right, wl, wr;
+  int dropout;
   size_t ws_bytes;
 };
 
@@ -142,6 +143,17 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     if (a.num_pages <= 0) return set_error("num_pages must be positive for a paged KV cache");
   }
   pl->kD = a.d > 128 ? 256 : ((a.d <= 64 && a.dtype != FA_B200_FP8_E4M3) ? 64 : 128);  // fp8 rows: one 128-byte panel
+  pl->dropout = a.p_dropout > 0.f;
+  if (a.p_dropout < 0.f || a.p_dropout >= 1.f) return set_error("p_dropout must be in [0, 1)");
+  if (pl->dropout) {
+    if (a.softcap > 0.f) return set_error("Softcapping does not support dropout for now");  // flash_api.cpp:391
+    if (mode == kKvcache || a.block_table) return set_error("dropout is not supported on the kvcache / paged path");
+    if (a.dtype == FA_B200_FP8_E4M3) return set_error("dropout is not supported for fp8 inputs");
+    if (a.num_splits > 1) return set_error("dropout is not supported with num_splits > 1");
+    if (a.pack_gqa == 1) return set_error("dropout is not supported with pack_gqa");
+  }
+  if (a.s_dmask && (mode == kKvcache || a.dtype == FA_B200_FP8_E4M3))
+    return set_error("return_softmax is only supported on the fp16 / bf16 dense and varlen forward");
   if (a.dtype == FA_B200_FP8_E4M3 && a.d % 16 != 0) return set_error("fp8 head_size should be a multiple of 16");
   // window canonicalisation (flash_api.cpp:414-419, set_params_fprop :150-164)
   int wl = a.window_size_left, wr = a.window_size_right;
@@ -168,6 +180,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     pl->tiles = (a.seqlen_q * (g > 1 && is_pow2(g) ? g : 1) <= 128 || est_blocks <= limit) ? 1 : 2;
     if (const char* e = getenv("FA_B200_FWD_TILES")) { if (e[0] == '1') pl->tiles = 1; if (e[0] == '2') pl->tiles = 2; }
     if (pl->kD == 256) pl->tiles = 1;  // S (128) + O (256) TMEM columns: one tile per CTA (forward only)
+    if (pl->dropout) pl->tiles = 1;    // the dropout kernels are only instantiated for the 1-tile configuration
   }
   const int rows_cta = 128 * pl->tiles;
   // GQA head packing: fold the g query heads of one KV head into the M dimension when a CTA's worth of query
@@ -176,7 +189,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   if (a.pack_gqa == 1 && g > 1) {
     if (!is_pow2(g) || g > 128) return set_error("pack_gqa needs a power-of-two group size <= 128");
     gp = g;
-  } else if (a.pack_gqa == 0 && g > 1 && is_pow2(g) && g <= 128) {
+  } else if (a.pack_gqa == 0 && g > 1 && is_pow2(g) && g <= 128 && !pl->dropout) {
     const int sq = a.seqlen_q;
     const double eff_unpacked = double(sq) / (cdiv(sq, rows_cta) * rows_cta);
     const double eff_packed = double(sq) * g / (cdiv(sq * g, rows_cta) * rows_cta);
@@ -187,7 +200,9 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   // split-KV (flash_api.cpp:317-347): heuristic when num_splits == 0; never for packed-varlen q
   int splits = a.num_splits;
   if (splits < 0) return set_error("num_splits must be non-negative");
-  if (mode == kVarlen) {
+  if (pl->dropout) {
+    splits = 1;  // flash_api.cpp:331: the reference only splits when p_dropout == 0
+  } else if (mode == kVarlen) {
     if (a.block_table && splits > 1) return set_error("num_splits > 1 is not supported for varlen paged KV");
     splits = 1;
   } else if (splits == 0) {
@@ -217,11 +232,11 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   return 0;
 }
 
-template <typename T, int kD, int kTiles>
+template <typename T, int kD, int kTiles, bool kDropout = false>
 static int launch_fwd_kernel_t(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
   using Cfg = FwdCfg<kD, EltInfo<T>::kBytes, kTiles>;
   static bool configured = false;
-  auto kern = fa_fwd_kernel<T, kD, kTiles>;
+  auto kern = fa_fwd_kernel<T, kD, kTiles, kDropout>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(fwd): ") + cudaGetErrorString(e));
@@ -235,7 +250,10 @@ static int launch_fwd_kernel_t(const FwdKernelParams& kp, dim3 grid, cudaStream_
 }
 
 template <typename T, int kD>
-static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream, int tiles) {
+static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream, int tiles, bool dropout = false) {
+  if constexpr (!EltInfo<T>::kFp8) {
+    if (dropout) return launch_fwd_kernel_t<T, kD, 1, true>(kp, grid, stream);
+  }
   return tiles == 1 ? launch_fwd_kernel_t<T, kD, 1>(kp, grid, stream) : launch_fwd_kernel_t<T, kD, 2>(kp, grid, stream);
 }
 
@@ -314,6 +332,7 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     kp.scale = a.softmax_scale;
   }
   kp.scale_log2 = kp.scale * float(M_LOG2E);
+  if (pl.dropout) kp.drop = make_dropout_params(a.p_dropout, a.philox_seed, a.philox_offset);
   if (pl.num_splits > 1) {
     const size_t rows = size_t(pl.num_splits) * a.b * a.h * a.seqlen_q;
     kp.o_accum = reinterpret_cast<float*>(a.workspace);
@@ -324,13 +343,15 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   if (fp8) {
     rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream, pl.tiles);
   } else if (a.dtype == FA_B200_BF16) {
-    rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream, pl.tiles)
-       : pl.kD == 128 ? launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream, pl.tiles)
-                      : launch_fwd_kernel_t<__nv_bfloat16, 256, 1>(kp, grid, stream);
+    rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream, pl.tiles, pl.dropout)
+       : pl.kD == 128 ? launch_fwd_kernel<__nv_bfloat16, 128>(kp, grid, stream, pl.tiles, pl.dropout)
+       : pl.dropout ? launch_fwd_kernel_t<__nv_bfloat16, 256, 1, true>(kp, grid, stream)
+                    : launch_fwd_kernel_t<__nv_bfloat16, 256, 1>(kp, grid, stream);
   } else {
-    rc = pl.kD == 64 ? launch_fwd_kernel<__half, 64>(kp, grid, stream, pl.tiles)
-       : pl.kD == 128 ? launch_fwd_kernel<__half, 128>(kp, grid, stream, pl.tiles)
-                      : launch_fwd_kernel_t<__half, 256, 1>(kp, grid, stream);
+    rc = pl.kD == 64 ? launch_fwd_kernel<__half, 64>(kp, grid, stream, pl.tiles, pl.dropout)
+       : pl.kD == 128 ? launch_fwd_kernel<__half, 128>(kp, grid, stream, pl.tiles, pl.dropout)
+       : pl.dropout ? launch_fwd_kernel_t<__half, 256, 1, true>(kp, grid, stream)
+                    : launch_fwd_kernel_t<__half, 256, 1>(kp, grid, stream);
   }
   if (rc) return rc;
   if (pl.num_splits > 1) {
@@ -352,6 +373,26 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     g_launch_count++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(std::string("fa_combine_kernel launch: ") + cudaGetErrorString(e));
+  }
+  if (a.s_dmask) {
+    DmaskParams dm;
+    memset(&dm, 0, sizeof dm);
+    dm.q = a.q; dm.k = a.k; dm.lse = a.softmax_lse; dm.s_out = a.s_dmask;
+    dm.q_batch_stride = a.q_batch_stride; dm.q_row_stride = a.q_row_stride; dm.q_head_stride = a.q_head_stride;
+    dm.k_batch_stride = a.k_batch_stride; dm.k_row_stride = a.k_row_stride; dm.k_head_stride = a.k_head_stride;
+    dm.cu_seqlens_q = a.cu_seqlens_q; dm.cu_seqlens_k = a.cu_seqlens_k;
+    dm.alibi_slopes = a.alibi_slopes; dm.alibi_batch_stride = a.alibi_slopes_batch_stride;
+    dm.b = a.b; dm.h = a.h; dm.h_k = a.h_k; dm.sq = a.seqlen_q; dm.sk = a.seqlen_k; dm.d = a.d;
+    dm.sq_r = (a.seqlen_q + 127) / 128 * 128; dm.sk_r = (a.seqlen_k + 127) / 128 * 128; dm.total_q = a.total_q;
+    dm.has_left = pl.has_left; dm.has_right = pl.has_right; dm.wl = pl.wl; dm.wr = pl.wr;
+    dm.scale = a.softmax_scale;
+    dm.drop = make_dropout_params(a.p_dropout, a.philox_seed, a.philox_offset);
+    dim3 dgrid((dm.sq_r + 7) / 8, a.h, a.b);
+    if (a.dtype == FA_B200_FP16) fa_dmask_kernel<__half><<<dgrid, 256, 0, stream>>>(dm);
+    else fa_dmask_kernel<__nv_bfloat16><<<dgrid, 256, 0, stream>>>(dm);
+    g_launch_count++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(std::string("fa_dmask_kernel launch: ") + cudaGetErrorString(e));
   }
   return 0;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <string>
 
@@ -15,4 +16,18 @@ int set_error(const std::string& msg);
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 int num_sms();
+}  // namespace fa
+
+#include "fa_dropout.cuh"
+namespace fa {
+// p_dropout -> 8-bit keep threshold and rescale factor (reference: flash_api.cpp:113-121)
+inline DropoutParams make_dropout_params(float p_dropout, uint64_t seed, uint64_t offset) {
+  DropoutParams dp;
+  const float p_keep = 1.f - p_dropout;
+  dp.seed_lo = uint32_t(seed); dp.seed_hi = uint32_t(seed >> 32);
+  dp.off_lo = uint32_t(offset); dp.off_hi = uint32_t(offset >> 32);
+  dp.thr = uint32_t(floorf(p_keep * 255.0f));
+  dp.rp = 1.f / p_keep;
+  return dp;
+}
 }  // namespace fa

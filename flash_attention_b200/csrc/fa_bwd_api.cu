@@ -29,6 +29,8 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   if (a.d <= 0 || a.d > 256) return set_error("FlashAttention backward only supports head dimension at most 256");
   if (a.d % 8 != 0) return set_error("head_size should be a multiple of 8");
   if (a.d > 128) return set_error("this build of fa_b200 supports head dimension at most 128");
+  if (a.p_dropout < 0.f || a.p_dropout >= 1.f) return set_error("p_dropout must be in [0, 1)");
+  if (a.p_dropout > 0.f && a.softcap > 0.f) return set_error("Softcapping does not support dropout for now");
   if (a.h <= 0 || a.h_k <= 0 || a.h % a.h_k != 0)
     return set_error("Number of heads in key/value must divide number of heads in query");
   if (varlen && (!a.cu_seqlens_q || !a.cu_seqlens_k)) return set_error("cu_seqlens_q and cu_seqlens_k are required");
@@ -48,11 +50,11 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   return 0;
 }
 
-template <typename T, int kD, bool kSoftcap>
+template <typename T, int kD, bool kSoftcap, bool kDropout = false>
 static int launch_bwd_main(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
   using Cfg = BwdCfg<kD>;
   static bool configured = false;
-  auto kern = fa_bwd_kernel<T, kD, kSoftcap>;
+  auto kern = fa_bwd_kernel<T, kD, kSoftcap, kDropout>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(bwd): ") + cudaGetErrorString(e));
@@ -123,7 +125,14 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   else { kp.softcap_pre = 0.f; kp.scale_eff = a.softmax_scale; }
   kp.scale_log2 = kp.scale_eff * float(M_LOG2E);
   dim3 grid((a.seqlen_k + 127) / 128, a.h_k, a.b);
-  int rc = a.softcap > 0.f ? launch_bwd_main<T, kD, true>(kp, grid, stream) : launch_bwd_main<T, kD, false>(kp, grid, stream);
+  int rc;
+  if (a.p_dropout > 0.f) {
+    kp.drop = make_dropout_params(a.p_dropout, a.philox_seed, a.philox_offset);
+    kp.rng_state = a.rng_state;
+    rc = launch_bwd_main<T, kD, false, true>(kp, grid, stream);
+  } else {
+    rc = a.softcap > 0.f ? launch_bwd_main<T, kD, true>(kp, grid, stream) : launch_bwd_main<T, kD, false>(kp, grid, stream);
+  }
   if (rc) return rc;
   {
     dim3 cgrid((a.seqlen_q + 7) / 8, a.h, a.b);

@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "fa_dropout.cuh"
 #include "fa_fwd_sm100.cuh"
 #include "fa_ptx.cuh"
 
@@ -50,6 +51,8 @@ struct BwdKernelParams {
   float scale_eff;           // scale of the logits inside exp: softcap if softcap > 0 else softmax_scale
   float scale_log2;          // scale_eff * log2(e)
   float softcap_pre;
+  DropoutParams drop;         // kDropout kernels only: the forward's rng_state and p_dropout
+  const uint64_t* rng_state;  // device copy of {seed, offset}; overrides drop.seed/off when non-null
 };
 
 #ifndef FA_BWD_DQ_FP16
@@ -166,7 +169,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
-template <typename T, int kD, bool kSoftcap>
+template <typename T, int kD, bool kSoftcap, bool kDropout = false>
 __global__ void __launch_bounds__(BwdCfg<kD>::kThreads, 1)
 fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   using Cfg = BwdCfg<kD>;
@@ -446,6 +449,14 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
     const int i_lo = p.has_right ? j - shift - p.wr : -(1 << 30);
     const int i_hi = p.has_left ? j - shift + p.wl : (1 << 30);
     const bool key_valid = j < sk_b;
+    DropoutParams drop = p.drop;
+    if constexpr (kDropout) {
+      if (p.rng_state) {
+        const uint64_t sd = p.rng_state[0], of = p.rng_state[1];
+        drop.seed_lo = uint32_t(sd); drop.seed_hi = uint32_t(sd >> 32);
+        drop.off_lo = uint32_t(of); drop.off_hi = uint32_t(of >> 32);
+      }
+    }
     for (int it = 0; it < n_iter; ++it) {
       const int hq = hk * p.g + it / n_m;
       const int m = m_min + it % n_m;
@@ -490,10 +501,30 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) pr[c] = (!key_valid || c < lo || c > hi) ? 0.f : pr[c];
       }
+      // dropout (dropout.h:apply_dropout): dV sees the thinned P, dS keeps the full P and thins dP instead
+      // (flash_bwd_kernel.h:560-596).  keep_lo/hi bit c = query q0 + c is kept for this key.
+      uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+      if constexpr (kDropout) {
+        keep_lo = keep_hi = 0u;
+        const int sh = 8 * (j & 3);
+        const uint32_t bh = uint32_t(bidb * p.h + hq);
+#pragma unroll
+        for (int c4 = 0; c4 < 64; c4 += 4) {
+          const uint4 rr = dropout_patch(drop, uint32_t(q0 + c4) >> 2, uint32_t(j) >> 2, bh);
+          uint32_t bits = (((rr.x >> sh) & 0xffu) <= drop.thr ? 1u : 0u) | (((rr.y >> sh) & 0xffu) <= drop.thr ? 2u : 0u) |
+                          (((rr.z >> sh) & 0xffu) <= drop.thr ? 4u : 0u) | (((rr.w >> sh) & 0xffu) <= drop.thr ? 8u : 0u);
+          if (c4 < 32) keep_lo |= bits << c4;
+          else keep_hi |= bits << (c4 - 32);
+        }
+      }
+      auto kept = [&](int c) { return ((c < 32 ? keep_lo >> c : keep_hi >> (c - 32)) & 1u) != 0u; };
       {
         uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) pk[c / 2] = Elt<T>::pack(pr[c], pr[c + 1]);
+        for (int c = 0; c < 64; c += 2) {
+          if constexpr (kDropout) pk[c / 2] = Elt<T>::pack(kept(c) ? pr[c] : 0.f, kept(c + 1) ? pr[c + 1] : 0.f);
+          else pk[c / 2] = Elt<T>::pack(pr[c], pr[c + 1]);
+        }
         tmem_st_x32(t_p, pk);
         tmem_wait_st();
         tc_fence_before();
@@ -513,10 +544,18 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
         for (int c4 = 0; c4 < 32; c4 += 4) {
           const int cc = h2 * 32 + c4;
           const float4 d4 = *reinterpret_cast<const float4*>(s_dps + cc);
-          float e0 = pr[cc + 0] * (__uint_as_float(du[c4 + 0]) - d4.x);
-          float e1 = pr[cc + 1] * (__uint_as_float(du[c4 + 1]) - d4.y);
-          float e2 = pr[cc + 2] * (__uint_as_float(du[c4 + 2]) - d4.z);
-          float e3 = pr[cc + 3] * (__uint_as_float(du[c4 + 3]) - d4.w);
+          float g0 = __uint_as_float(du[c4 + 0]), g1 = __uint_as_float(du[c4 + 1]);
+          float g2 = __uint_as_float(du[c4 + 2]), g3 = __uint_as_float(du[c4 + 3]);
+          if constexpr (kDropout) {
+            g0 = kept(cc + 0) ? g0 * drop.rp : 0.f;
+            g1 = kept(cc + 1) ? g1 * drop.rp : 0.f;
+            g2 = kept(cc + 2) ? g2 * drop.rp : 0.f;
+            g3 = kept(cc + 3) ? g3 * drop.rp : 0.f;
+          }
+          float e0 = pr[cc + 0] * (g0 - d4.x);
+          float e1 = pr[cc + 1] * (g1 - d4.y);
+          float e2 = pr[cc + 2] * (g2 - d4.z);
+          float e3 = pr[cc + 3] * (g3 - d4.w);
           if constexpr (kSoftcap) {  // d tanh(x) = 1 - tanh^2 (utils.h:403-409); undo the ALiBi bias first
             float t0 = s[cc + 0], t1 = s[cc + 1], t2 = s[cc + 2], t3 = s[cc + 3];
             if (p.alibi_slopes) {
@@ -558,7 +597,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const uint32_t t_src = (which == 0 ? tDV : tDK) + lane_sel;
-      const float mul = which == 0 ? 1.0f : p.scale;
+      const float mul = which == 0 ? (kDropout ? drop.rp : 1.0f) : p.scale;
       T* base = reinterpret_cast<T*>(which == 0 ? p.dv : p.dk) +
                 int64_t(bk) * (which == 0 ? p.dv_batch_stride : p.dk_batch_stride) +
                 int64_t(k_off + j) * (which == 0 ? p.dv_row_stride : p.dk_row_stride) +

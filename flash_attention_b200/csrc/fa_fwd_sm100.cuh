@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "fa_dropout.cuh"
 #include "fa_ptx.cuh"
 
 namespace fa {
@@ -61,6 +62,7 @@ struct FwdKernelParams {
   float scale;              // effective softmax scale (softcap if softcap > 0)
   float scale_log2;         // scale * log2(e)
   float softcap_pre;        // softmax_scale / softcap, 0 = off
+  DropoutParams drop;       // kDropout kernels only
 };
 
 // kTiles = 2: the throughput configuration (256 query rows per CTA, 5-stage K/V ring, one CTA per SM).
@@ -119,7 +121,7 @@ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; 
 #define FA_FWD_POLY_PAIRS 1  // measured on B200 (r01): 0 -> 1315, 1 -> 1339, 2 -> 1307, 3 -> 1147, 4 -> 1046 TFLOP/s fwd
 #endif
 
-template <typename T, int kD, int kTiles>
+template <typename T, int kD, int kTiles, bool kDropout = false>
 __global__ void __launch_bounds__((FwdCfg<kD, 2, kTiles>::kThreads), (FwdCfg<kD, 2, kTiles>::kCtasPerSm))
 fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   constexpr int kBytes = EltInfo<T>::kBytes;
@@ -515,6 +517,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int cc = 0; cc < 128; cc += 32) {
           uint32_t pk[16];
           float ee[4];
+          uint32_t keep_w = 0;
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             float x0, x1, e0, e1;
@@ -527,6 +530,15 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             if (c & 2) acc_b = add2(acc_b, pack2(e0, e1));
             else acc_a = add2(acc_a, pack2(e0, e1));
+            if constexpr (kDropout) {
+              // the row sum keeps the undropped probabilities (softmax.h:128-187 runs before dropout.h:apply_dropout);
+              // only the P that feeds P V is thinned, and 1/p_keep is folded into the final normalisation
+              if ((c & 2) == 0)
+                keep_w = select_word(dropout_patch(p.drop, uint32_t(qpos) >> 2, uint32_t(col0 + cc + c) >> 2,
+                                                   uint32_t(bidb * p.h + head)), qpos & 3);
+              e0 = ((keep_w >> (8 * (c & 2))) & 0xffu) <= p.drop.thr ? e0 : 0.f;
+              e1 = ((keep_w >> (8 * (c & 2) + 8)) & 0xffu) <= p.drop.thr ? e1 : 0.f;
+            }
             if constexpr (kFp8) {
               ee[c & 2] = e0;
               ee[(c & 2) + 1] = e1;
@@ -557,6 +569,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       const bool dead = !(row_sum > 0.f);  // also catches NaN
       if (!dead) {
         inv = descale_v / row_sum;
+        if constexpr (kDropout) inv *= p.drop.rp;  // dropout.h:apply_dropout rescale, folded into the normalisation
         lse_val = m_ref * scale_eff + __logf(row_sum) - kPOffset * 0.6931471805599453f;
       } else {
         // fully masked row: +inf for a final result, -inf for a split partial

@@ -68,15 +68,33 @@ def _workspace(lib, args, device):
     return ws
 
 
+def _round128(x: int) -> int:
+    return (x + 127) // 128 * 128
+
+
+def _dropout_state(a, p_dropout, gen_, device, b, h):
+    """Philox (seed, offset) of this call from the CUDA generator, advanced like the reference does
+    (flash_api.cpp:505-517: counter_offset = b * h * 32).  Returns the `rng_state` tensor (2,) int64."""
+    _check(0.0 <= p_dropout < 1.0, "p_dropout must be in [0, 1)")
+    if p_dropout == 0.0:
+        return torch.zeros(2, dtype=torch.int64, device=device)
+    gen = gen_ if gen_ is not None else torch.cuda.default_generators[device.index if device.index is not None
+                                                                       else torch.cuda.current_device()]
+    seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+    gen.set_offset(offset + b * h * 32)
+    a.p_dropout, a.philox_seed, a.philox_offset = p_dropout, seed & (2**64 - 1), offset
+    wrap = lambda x: x - 2**64 if x >= 2**63 else x  # noqa: E731  (int64 storage of the uint64 seed)
+    return torch.tensor([wrap(seed & (2**64 - 1)), offset], dtype=torch.int64).to(device, non_blocking=True)
+
+
 # --------------------------------------------------------------------------------------- fwd
 def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, window_size_left, window_size_right,
         softcap, return_softmax, gen_=None) -> List[torch.Tensor]:
     """mha_fwd (flash_api.cpp:368-536).  q (b,sq,h,d), k/v (b,sk,h_k,d) -> [out, softmax_lse(b,h,sq), p, rng_state]."""
     lib = _lib.load()
     _common_checks(q, k, v)
-    _check(gen_ is None, "Passing a generator is not supported; fa_b200 has no dropout")
-    _check(p_dropout == 0.0, "fa_b200: dropout is not implemented (p_dropout must be 0)")
-    _check(not return_softmax, "return_softmax is only supported when p_dropout > 0.0")
+    if return_softmax:
+        _check(p_dropout > 0.0, "return_softmax is only supported when p_dropout > 0.0")
     _check(q.dim() == 4 and k.dim() == 4 and v.dim() == 4, "q, k, v must be 4-D (batch, seqlen, nheads, headdim)")
     b, sq, h, d = q.shape
     sk, hk = k.shape[1], k.shape[2]
@@ -97,14 +115,17 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
         out = torch.empty_like(q)
     lse = torch.empty((b, h, sq), dtype=torch.float32, device=q.device)
     p = torch.empty(0, dtype=q.dtype, device=q.device)
-    rng_state = torch.zeros(2, dtype=torch.int64, device=q.device)
+    a = _lib.FwdArgs()
+    rng_state = _dropout_state(a, p_dropout, gen_, q.device, b, h)
     if sq == 0:
         return [out, lse, p, rng_state]
     if sk == 0:  # flash_api.cpp:521-528
         out.zero_()
         lse.fill_(float("inf"))
         return [out, lse, p, rng_state]
-    a = _lib.FwdArgs()
+    if return_softmax:  # (b, h, seqlen_q_rounded, seqlen_k_rounded), flash_api.cpp:466-470
+        p = torch.empty((b, h, _round128(sq), _round128(sk)), dtype=q.dtype, device=q.device)
+        a.s_dmask = _ptr(p)
     a.q, a.k, a.v, a.out, a.softmax_lse = _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse)
     a.q_batch_stride, a.q_row_stride, a.q_head_stride = q.stride(0), q.stride(1), q.stride(2)
     a.k_batch_stride, a.k_row_stride, a.k_head_stride = k.stride(0), k.stride(1), k.stride(2)
@@ -225,9 +246,8 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_,
     (num_blocks,page,h_k,d) with block_table (b,max_blocks) -> [out, softmax_lse(h,total_q), p, rng_state]."""
     lib = _lib.load()
     _common_checks(q, k, v)
-    _check(gen_ is None, "Passing a generator is not supported; fa_b200 has no dropout")
-    _check(p_dropout == 0.0, "fa_b200: dropout is not implemented (p_dropout must be 0)")
-    _check(not return_softmax, "return_softmax is only supported when p_dropout > 0.0")
+    if return_softmax:
+        _check(p_dropout > 0.0, "return_softmax is only supported when p_dropout > 0.0")
     _check(leftpad_k_ is None, "fa_b200: leftpad_k is not implemented")
     _check(cu_seqlens_q.dtype == torch.int32, "cu_seqlens_q must have dtype int32")
     _check(cu_seqlens_k.dtype == torch.int32, "cu_seqlens_k must have dtype int32")
@@ -258,7 +278,11 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_,
         out = torch.empty_like(q)
     lse = torch.empty((h, total_q), dtype=torch.float32, device=q.device)
     p = torch.empty(0, dtype=q.dtype, device=q.device)
-    rng_state = torch.zeros(2, dtype=torch.int64, device=q.device)
+    a = _lib.FwdArgs()
+    if p_dropout > 0.0:
+        _check(not paged and seqused_k is None and seqused_q is None,
+               "dropout is not supported together with paged KV / seqused")
+    rng_state = _dropout_state(a, p_dropout, gen_, q.device, b, h)
     if zero_tensors:
         out.zero_()
         lse.fill_(float("-inf"))
@@ -268,7 +292,9 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_,
         out.zero_()
         lse.fill_(float("inf"))
         return [out, lse, p, rng_state]
-    a = _lib.FwdArgs()
+    if return_softmax:  # flash_api.cpp:690-694
+        p = torch.zeros((b, h, _round128(max_seqlen_q), _round128(max_seqlen_k)), dtype=q.dtype, device=q.device)
+        a.s_dmask = _ptr(p)
     a.q, a.k, a.v, a.out, a.softmax_lse = _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse)
     a.q_batch_stride, a.q_row_stride, a.q_head_stride = 0, q.stride(0), q.stride(1)
     a.o_batch_stride, a.o_row_stride, a.o_head_stride = 0, out.stride(0), out.stride(1)
@@ -414,13 +440,24 @@ def _alloc_or_check(t_, like, name):
     return t_
 
 
+def _bwd_dropout(a, p_dropout, rng_state, softcap):
+    """p_dropout + the forward's rng_state (flash_api.cpp:990-1003); the kernel reads (seed, offset) from the device tensor."""
+    _check(0.0 <= p_dropout < 1.0, "p_dropout must be in [0, 1)")
+    if p_dropout == 0.0:
+        return
+    _check(softcap == 0.0, "Softcapping does not support dropout for now")
+    _check(rng_state is not None, "fa_b200: the backward of a dropout forward needs its rng_state")
+    _check(rng_state.is_cuda and rng_state.dtype == torch.int64 and rng_state.numel() == 2 and rng_state.is_contiguous(),
+           "rng_state must be a contiguous CUDA int64 tensor of 2 elements")
+    a.p_dropout = p_dropout
+    a.rng_state = _ptr(rng_state)
+
+
 def bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, alibi_slopes_, p_dropout, softmax_scale, is_causal,
         window_size_left, window_size_right, softcap, deterministic, gen_=None, rng_state=None) -> List[torch.Tensor]:
     """mha_bwd (flash_api.cpp:800-1008) -> [dq, dk, dv, softmax_d(b,h,round128(sq))]."""
     lib = _lib.load()
     _common_checks(q, k, v)
-    _check(gen_ is None, "Passing a generator is not supported; fa_b200 has no dropout")
-    _check(p_dropout == 0.0, "fa_b200: dropout is not implemented (p_dropout must be 0)")
     _check(dout.dtype == q.dtype and out.dtype == q.dtype, "query and dout/out must have the same dtype")
     _check(dout.stride(-1) == 1 and out.stride(-1) == 1, "dout/out tensor must have contiguous last dimension")
     b, sq, h, d = q.shape
@@ -440,6 +477,7 @@ def bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, alibi_slopes_, p_dropout
         return [dq, dk, dv, softmax_d]
     a = _lib.BwdArgs()
     a.softmax_d = _ptr(softmax_d)
+    _bwd_dropout(a, p_dropout, rng_state, softcap)
     for name, t in (("q", q), ("k", k), ("v", v), ("o", out), ("do", dout), ("dq", dq), ("dk", dk), ("dv", dv)):
         setattr(a, name + "_batch_stride", t.stride(0))
         setattr(a, name + "_row_stride", t.stride(1))
@@ -458,8 +496,6 @@ def varlen_bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, cu_seqlens_q, cu_
     """mha_varlen_bwd (flash_api.cpp:1010-1241) -> [dq, dk, dv, softmax_d(h, total_q + 128*b)]."""
     lib = _lib.load()
     _common_checks(q, k, v)
-    _check(gen_ is None, "Passing a generator is not supported; fa_b200 has no dropout")
-    _check(p_dropout == 0.0, "fa_b200: dropout is not implemented (p_dropout must be 0)")
     _check(cu_seqlens_q.dtype == torch.int32 and cu_seqlens_k.dtype == torch.int32, "cu_seqlens must have dtype int32")
     total_q, h, d = q.shape
     total_k, hk = k.shape[0], k.shape[1]
@@ -479,6 +515,7 @@ def varlen_bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, cu_seqlens_q, cu_
         return [dq, dk, dv, softmax_d]
     a = _lib.BwdArgs()
     a.softmax_d = _ptr(softmax_d)
+    _bwd_dropout(a, p_dropout, rng_state, softcap)
     for name, t in (("q", q), ("k", k), ("v", v), ("o", out), ("do", dout), ("dq", dq), ("dk", dk), ("dv", dv)):
         setattr(a, name + "_batch_stride", 0)
         setattr(a, name + "_row_stride", t.stride(0))

@@ -29,20 +29,21 @@ class _FlashAttnFunc(torch.autograd.Function):
         d = q.shape[-1]
         qp, kp, vp = (_c(_pad8(t, d)) for t in (q, k, v))
         out_p, lse, S_dmask, rng_state = _op.fwd(qp, kp, vp, None, alibi_slopes, dropout_p, softmax_scale, causal,
-                                                 window_size[0], window_size[1], softcap, False, None)
-        ctx.save_for_backward(qp, kp, vp, out_p, lse)
+                                                 window_size[0], window_size[1], softcap,
+                                                 return_softmax and dropout_p > 0, None)
+        ctx.save_for_backward(qp, kp, vp, out_p, lse, rng_state)
         ctx.args = (dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d)
         out = out_p[..., :d]
         return (out, lse, S_dmask) if return_softmax else out
 
     @staticmethod
     def backward(ctx, dout, *unused):
-        qp, kp, vp, out_p, lse = ctx.saved_tensors
+        qp, kp, vp, out_p, lse, rng_state = ctx.saved_tensors
         dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d = ctx.args
         dq, dk, dv = torch.empty_like(qp), torch.empty_like(kp), torch.empty_like(vp)
         dout_p = _c(_pad8(dout, d))
         _op.bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, alibi_slopes, dropout_p, softmax_scale, causal,
-                window_size[0], window_size[1], softcap, deterministic, None, None)
+                window_size[0], window_size[1], softcap, deterministic, None, rng_state)
         return dq[..., :d], dk[..., :d], dv[..., :d], None, None, None, None, None, None, None, None
 
 
@@ -56,20 +57,22 @@ class _FlashAttnVarlenFunc(torch.autograd.Function):
         qp, kp, vp = (_c(_pad8(t, d)) for t in (q, k, v))
         out_p, lse, S_dmask, rng_state = _op.varlen_fwd(qp, kp, vp, None, cu_q, cu_k, None, None, block_table,
                                                         alibi_slopes, max_q, max_k, dropout_p, softmax_scale, False,
-                                                        causal, window_size[0], window_size[1], softcap, False, None)
-        ctx.save_for_backward(qp, kp, vp, out_p, lse, cu_q, cu_k)
+                                                        causal, window_size[0], window_size[1], softcap,
+                                                        return_softmax and dropout_p > 0, None)
+        ctx.save_for_backward(qp, kp, vp, out_p, lse, cu_q, cu_k, rng_state)
         ctx.args = (max_q, max_k, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d)
         out = out_p[..., :d]
         return (out, lse, S_dmask) if return_softmax else out
 
     @staticmethod
     def backward(ctx, dout, *unused):
-        qp, kp, vp, out_p, lse, cu_q, cu_k = ctx.saved_tensors
+        qp, kp, vp, out_p, lse, cu_q, cu_k, rng_state = ctx.saved_tensors
         max_q, max_k, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d = ctx.args
         dq, dk, dv = torch.empty_like(qp), torch.empty_like(kp), torch.empty_like(vp)
         dout_p = _c(_pad8(dout, d))
         _op.varlen_bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, cu_q, cu_k, alibi_slopes, max_q, max_k, dropout_p,
-                       softmax_scale, False, causal, window_size[0], window_size[1], softcap, deterministic, None, None)
+                       softmax_scale, False, causal, window_size[0], window_size[1], softcap, deterministic, None,
+                       rng_state)
         return (dq[..., :d], dk[..., :d], dv[..., :d]) + (None,) * 13
 
 

@@ -89,6 +89,14 @@ typedef struct fa_b200_fwd_args {
   void* workspace; size_t workspace_bytes;
   /* debugging: optional fp32 buffer (128x128) receiving the raw S tile of CTA (0,0,0) */
   float* debug_s;
+  /* attention dropout (mha_fwd's p_dropout / rng_state, flash_api.cpp:370,505-517): Philox4x32-7 keyed by
+   * (philox_seed, philox_offset) -- the two int64 the reference returns as `rng_state`.  0 = off.
+   * Not available for kvcache, fp8, split-KV or together with softcap (flash_api.cpp:391). */
+  float p_dropout;
+  uint64_t philox_seed, philox_offset;
+  /* return_softmax: optional (b, h, round128(seqlen_q), round128(seqlen_k)) buffer in q's dtype receiving the
+   * normalised probabilities, negated where dropped ("for testing only", flash_attn_interface.py:1196) */
+  void* s_dmask;
 } fa_b200_fwd_args;
 
 typedef struct fa_b200_bwd_args {
@@ -113,6 +121,11 @@ typedef struct fa_b200_bwd_args {
   int32_t is_causal; int32_t window_size_left, window_size_right;
   int32_t deterministic;
   void* workspace; size_t workspace_bytes;
+  /* dropout of the forward being differentiated: p_dropout and its rng_state (flash_api.cpp:810,990-1003).
+   * `rng_state` (device pointer to {seed, offset}, the tensor the forward returned) wins over the two host values */
+  float p_dropout;
+  uint64_t philox_seed, philox_offset;
+  const uint64_t* rng_state;
 } fa_b200_bwd_args;
 
 /* ---- forward ---- */

@@ -123,6 +123,8 @@ def attention_oracle(
     k_descale: Optional[torch.Tensor] = None,
     v_descale: Optional[torch.Tensor] = None,
     lse_masked_value: float = float("inf"),
+    dropout_p: float = 0.0,
+    dropout_mask: Optional[torch.Tensor] = None,  # (b, h, sq, sk) bool, True = keep (tests/test_flash_attn.py:231,288-296)
 ):
     """Returns (out (b,sq,h,dv) in q's dtype [bf16 if q is fp8], lse (b,h,sq) fp32).
 
@@ -168,12 +170,63 @@ def attention_oracle(
         o = torch.einsum("bhij,bjhd->bihd", p, vf) / denom.clamp_min(1e-30).permute(0, 2, 1, 3).to(compute_dtype)
     else:
         p = (e / denom.clamp_min(1e-30)).to(compute_dtype)
+        if dropout_mask is not None:  # attention_ref: masked_fill(~dropout_mask, 0) * 1/(1-p)
+            p = p.masked_fill(~dropout_mask, 0.0) * (1.0 / (1.0 - dropout_p))
         o = torch.einsum("bhij,bjhd->bihd", p, vf)
     o = o.masked_fill(dead.permute(0, 2, 1).unsqueeze(-1), 0.0)
     if q_lens is not None:
         qvalid = torch.arange(sq, device=q.device).view(1, sq) < q_lens.view(-1, 1)
         o = o.masked_fill(~qvalid.view(b, sq, 1, 1), 0.0)
     return o.to(out_dtype), lse
+
+
+_PHILOX_M0, _PHILOX_M1, _PHILOX_W0, _PHILOX_W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_7(c0, c1, c2, c3, k0, k1, rounds: int = 7):
+    """Philox4x32 with 7 rounds (the reference's generator, csrc/flash_attn/src/philox.cuh:29-51; Salmon et al.
+    SC'11) on numpy uint64 arrays holding 32-bit values.  Returns the four output words."""
+    import numpy as np
+
+    m32 = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) & m32 for x in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0 & 0xFFFFFFFF), np.uint64(k1 & 0xFFFFFFFF)
+    for _ in range(rounds):
+        p0 = np.uint64(_PHILOX_M0) * c0
+        p1 = np.uint64(_PHILOX_M1) * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & m32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & m32, lo1, (hi0 ^ c3 ^ k1) & m32, lo0
+        k0 = (k0 + np.uint64(_PHILOX_W0)) & m32
+        k1 = (k1 + np.uint64(_PHILOX_W1)) & m32
+    return c0, c1, c2, c3
+
+
+def philox_keep_mask(seed: int, offset: int, p_dropout: float, b: int, h: int, sq: int, sk: int) -> torch.Tensor:
+    """The library's dropout mask, restated on the CPU: (b, h, sq, sk) bool, True = keep.
+
+    Mapping (flash_attention_b200/csrc/fa_dropout.cuh): one Philox call per 4x4 patch of the (query, key)
+    matrix of a (batch, head): counter = (query//4, key//4, batch*h + head, offset_lo), key = (seed_lo,
+    seed_hi ^ offset_hi); output word (query % 4), byte (key % 4) is the element's random byte; keep iff
+    byte <= floor((1 - p_dropout) * 255) (8-bit threshold: csrc/flash_attn/src/dropout.h:17)."""
+    import numpy as np
+
+    seed &= 2**64 - 1
+    offset &= 2**64 - 1
+    thr = int(np.floor(np.float32(1.0 - p_dropout) * np.float32(255.0)))
+    nq4, nk4 = (sq + 3) // 4, (sk + 3) // 4
+    bh = np.arange(b * h, dtype=np.uint64).reshape(-1, 1, 1)
+    q4 = np.arange(nq4, dtype=np.uint64).reshape(1, -1, 1)
+    k4 = np.arange(nk4, dtype=np.uint64).reshape(1, 1, -1)
+    shape = (b * h, nq4, nk4)
+    words = philox4x32_7(np.broadcast_to(q4, shape), np.broadcast_to(k4, shape), np.broadcast_to(bh, shape),
+                         np.full(shape, offset & 0xFFFFFFFF, dtype=np.uint64), seed & 0xFFFFFFFF,
+                         ((seed >> 32) ^ (offset >> 32)) & 0xFFFFFFFF)
+    # (bh, q4, k4, word=query%4, byte=key%4)
+    w = np.stack(words, axis=-1)
+    by = np.stack([(w >> np.uint64(8 * j)) & np.uint64(0xFF) for j in range(4)], axis=-1)
+    keep = (by <= np.uint64(thr)).transpose(0, 1, 3, 2, 4).reshape(b * h, nq4 * 4, nk4 * 4)[:, :sq, :sk]
+    return torch.from_numpy(np.ascontiguousarray(keep)).view(b, h, sq, sk)
 
 
 def attention_oracle_bwd(q, k, v, dout, **kw):
