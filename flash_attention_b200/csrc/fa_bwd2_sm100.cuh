@@ -1,0 +1,541 @@
+// fa_bwd2_sm100.cuh — backward main loop on a CTA PAIR (cluster of 2, tcgen05 cta_group::2), head dim 128.
+//
+// Why: the single-CTA kernel (fa_bwd_sm100.cuh) is bound by shared-memory bandwidth, not by the tensor pipe:
+// per 128x128 tile it moves ~480 KB through shared memory (5 SS/TS MMAs read 256 KB of operands, Q/dO arrive by
+// TMA, dS and the fp32 dQ tile are staged) = 3750 clk at 128 B/clk against 2560 clk of MMA.  A pair MMA reads
+// each CTA's half of the B operand once for both CTAs, and the pair produces ONE dQ tile per 256 keys:
+//
+//   two CTAs = two adjacent 128-key blocks of one (batch, kv head), iterating the same (q head, query block) list
+//   S^T  = K Q^T       pair SS  M=256 (128 keys / CTA)  N=128 queries   B: CTA r holds query rows [64r, 64r+64)
+//   dP^T = V dO^T      pair SS  same shape
+//   dV  += P^T dO      pair TS  M=256  N=128 (d)                        B: CTA r holds d columns [64r, 64r+64)
+//   dK  += dS^T Q      pair TS  same shape
+//   dQ   = dS K        pair SS  M=128 (64 queries / CTA)  N=128 (d)  K-dim = 256 keys of the pair
+//                      A: CTA r holds dS^T[256 keys, query half r] -- the half computed by the peer arrives through
+//                      distributed shared memory (st.shared::cluster);  B: CTA r holds K[256 keys, d half r]
+//   per CTA and tile: 64 KB TMA + 192 KB MMA operand reads + 32 KB dS + 64 KB dQ staging = 352 KB (was 480 KB);
+//   the dQ reduce-add traffic to L2 halves as well.
+//
+// Same semantics, statistics, masks, dropout, GQA loop and epilogue as fa_bwd_kernel (reference:
+// csrc/flash_attn/src/flash_bwd_kernel.h:80-795); TMEM layouts of pair MMAs measured with
+// experiments/cta_pair_probe.cu (see fa_ptx.cuh).
+#pragma once
+#include "fa_bwd_sm100.cuh"
+
+namespace fa {
+
+struct Bwd2Cfg {
+  static constexpr int kThreads = 512;
+  static constexpr int kRegsCompute = 160, kRegsDrain = 96, kRegsOther = 96;
+  static constexpr int kSK = 0;                  // own K block   (128 keys x 128 d)   K-major A of S^T
+  static constexpr int kSV = kSK + 32768;        // own V block                         K-major A of dP^T
+  static constexpr int kSKt = kSV + 32768;       // K[256 pair keys, d half r]          MN-major B of dQ
+  static constexpr int kSQb = kSKt + 32768;      // Q[query half r, all d] 2 x (64 x 128 B)   K-major B of S^T
+  static constexpr int kSQg = kSQb + 16384;      // Q[128 queries, d half r]                   MN-major B of dK
+  static constexpr int kSDOb = kSQg + 16384;     // dO[query half r, all d]                    K-major B of dP^T
+  static constexpr int kSDOg = kSDOb + 16384;    // dO[128 queries, d half r]                  MN-major B of dV
+  static constexpr int kSDS = kSDOg + 16384;     // dS^T[256 pair keys, query half r]          MN-major A of dQ
+  static constexpr int kSDQ = kSDS + 32768;      // dQ staging: 4 chunks of 64 rows x 32 fp32
+  static constexpr int kSStat = kSDQ + 32768;    // lse_log2[2][128], dpsum[2][128]
+  static constexpr int kSBar = kSStat + 2048;
+  static constexpr int kNumBars = 20;
+  static constexpr int kSmemBytes = kSBar + 8 * kNumBars + 16;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <typename T, bool kSoftcap, bool kDropout>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Bwd2Cfg::kThreads, 1)
+fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
+  using Cfg = Bwd2Cfg;
+  constexpr int kD = 128;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, hk = blockIdx.y, bidb = blockIdx.z;
+  int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
+  if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
+  if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
+  const int pkey0 = pair * 256;
+  if (pkey0 >= sk_b) return;  // the whole pair lies beyond this sequence: both CTAs leave before any cluster operation
+  const int key0 = pkey0 + 128 * int(rank);
+  const int n_block = 2 * pair + int(rank);
+  const int shift = sk_b - sq_b;
+  const int m_total = (sq_b + 127) / 128;
+  // query-block range of the PAIR = union of its key blocks' ranges; a block outside its own range sees a fully
+  // masked tile (P = dS = 0), which keeps the two CTAs in lock step
+  int m_min = 0, m_max = m_total;
+  if (p.has_right) {
+    const int lo = pkey0 - shift - p.wr;
+    m_min = lo <= 0 ? 0 : lo / 128;
+  }
+  if (p.has_left) {
+    const int last_key0 = pkey0 + 128 < sk_b ? pkey0 + 128 : pkey0;
+    const int hi = last_key0 + 127 - shift + p.wl;
+    const int nb = hi < 0 ? 0 : hi / 128 + 1;
+    m_max = nb < m_max ? nb : m_max;
+  }
+  const int n_m = m_max > m_min ? m_max - m_min : 0;
+  const int n_iter = n_m * p.g;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  uint8_t* smem_gen = smem_raw;
+  const uint32_t sK = smem_base + Cfg::kSK, sV = smem_base + Cfg::kSV, sKt = smem_base + Cfg::kSKt;
+  const uint32_t sQb = smem_base + Cfg::kSQb, sQg = smem_base + Cfg::kSQg;
+  const uint32_t sDOb = smem_base + Cfg::kSDOb, sDOg = smem_base + Cfg::kSDOg;
+  const uint32_t sDS = smem_base + Cfg::kSDS, sDQ = smem_base + Cfg::kSDQ;
+  const uint32_t sStat = smem_base + Cfg::kSStat, sBar = smem_base + Cfg::kSBar;
+  // F_*: "operand landed" barriers, live in the LEADER (rank 0) and collect the TMA bytes of both CTAs
+  // E_*: "operand consumed" barriers, one per CTA, signalled by multicast tcgen05.commit
+  enum { F_KV = 0, F_QB = 1, F_DOB = 2, F_DOG = 3, F_QG = 4, E_QB = 5, E_DOB = 6, E_DOG = 7, E_QG = 8, F_ST0 = 9,
+         F_ST1 = 10, S_F = 11, DP_F = 12, P_F = 13, DS_F = 14, DQ_F = 15, DQ_E = 16, DKV_F = 17, DS_IN = 18, DS_PEER = 19 };
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSBar + 8 * Cfg::kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_do); tma_prefetch_desc(&p.tm_k); tma_prefetch_desc(&p.tm_v);
+    tma_prefetch_desc(&p.tm_q64); tma_prefetch_desc(&p.tm_do64); tma_prefetch_desc(&p.tm_dq64);
+  }
+  if (warp == 12) {
+    if (lane == 0) {
+      mbar_init(bar(F_KV), 1);
+      mbar_init(bar(F_QB), 1); mbar_init(bar(F_DOB), 1); mbar_init(bar(F_DOG), 1); mbar_init(bar(F_QG), 1);
+      mbar_init(bar(E_QB), 1); mbar_init(bar(E_DOB), 1); mbar_init(bar(E_DOG), 1); mbar_init(bar(E_QG), 1);
+      mbar_init(bar(F_ST0), 1); mbar_init(bar(F_ST1), 1);
+      mbar_init(bar(S_F), 1); mbar_init(bar(DP_F), 1);
+      mbar_init(bar(P_F), 16); mbar_init(bar(DS_F), 16);   // 8 compute warps of each CTA
+      mbar_init(bar(DQ_F), 1); mbar_init(bar(DQ_E), 8);    // 4 drain warps of each CTA
+      mbar_init(bar(DKV_F), 1);
+      mbar_init(bar(DS_IN), 4);     // the 4 local writer warps of sDS (+ 16 KB of st.async tx-bytes from the peer)
+      mbar_init(bar(DS_PEER), 1);   // leader only: the peer's sDS is complete (relayed by the peer's warp 12)
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(sTmemPtr, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised, both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 384;
+
+  if (warp >= 12) {
+    reg_dealloc<Cfg::kRegsOther>();
+    // ================================================================ TMA producer (one per CTA)
+    if (warp == 13) {
+      if (elect_one()) {
+        const int bk = p.cu_seqlens_k ? 0 : bidb, bq = p.cu_seqlens_q ? 0 : bidb;
+        const uint32_t fKV = mapa_rank(bar(F_KV), 0), fQB = mapa_rank(bar(F_QB), 0), fDOB = mapa_rank(bar(F_DOB), 0);
+        const uint32_t fDOG = mapa_rank(bar(F_DOG), 0), fQG = mapa_rank(bar(F_QG), 0);
+        const int dcol = 64 * int(rank);
+        if (rank == 0) mbar_arrive_expect_tx(bar(F_KV), 2 * 3 * 32768);
+#pragma unroll
+        for (int pn = 0; pn < 2; ++pn) {
+          tma_load_4d_pair(sK + pn * 16384, &p.tm_k, fKV, pn * 64, k_off + key0, hk, bk);
+          tma_load_4d_pair(sV + pn * 16384, &p.tm_v, fKV, pn * 64, k_off + key0, hk, bk);
+          tma_load_4d_pair(sKt + pn * 16384, &p.tm_k, fKV, dcol, k_off + pkey0 + 128 * pn, hk, bk);
+        }
+        for (int it = 0; it < n_iter; ++it) {
+          const int hq = hk * p.g + it / n_m;
+          const int m = m_min + it % n_m;
+          const int st = it & 1;
+          const int qrow = q_off + m * 128;
+          const int64_t srow = (int64_t(bidb) * p.h + hq) * p.sq_r + m * 128;
+          const uint32_t free_par = (it & 1) ^ 1;
+          mbar_wait(bar(E_QB), free_par, 400);     // S^T of the previous iteration has read sQb
+          if (rank == 0) mbar_arrive_expect_tx(bar(F_QB), 2 * 16384);
+          tma_load_4d_pair(sQb, &p.tm_q64, fQB, 0, qrow + 64 * int(rank), hq, bq);
+          tma_load_4d_pair(sQb + 8192, &p.tm_q64, fQB, 64, qrow + 64 * int(rank), hq, bq);
+          // row statistics of this query block (all 128 rows) for this CTA's compute warps
+          mbar_arrive_expect_tx(bar(F_ST0 + st), 1024);
+          bulk_load_1d(sStat + st * 512, p.lse_log2 + srow, 512, bar(F_ST0 + st));
+          bulk_load_1d(sStat + 1024 + st * 512, p.dpsum + srow, 512, bar(F_ST0 + st));
+          mbar_wait(bar(E_DOB), free_par, 401);
+          if (rank == 0) mbar_arrive_expect_tx(bar(F_DOB), 2 * 16384);
+          tma_load_4d_pair(sDOb, &p.tm_do64, fDOB, 0, qrow + 64 * int(rank), hq, bq);
+          tma_load_4d_pair(sDOb + 8192, &p.tm_do64, fDOB, 64, qrow + 64 * int(rank), hq, bq);
+          mbar_wait(bar(E_DOG), free_par, 402);
+          if (rank == 0) mbar_arrive_expect_tx(bar(F_DOG), 2 * 16384);
+          tma_load_4d_pair(sDOg, &p.tm_do, fDOG, dcol, qrow, hq, bq);
+          mbar_wait(bar(E_QG), free_par, 403);
+          if (rank == 0) mbar_arrive_expect_tx(bar(F_QG), 2 * 16384);
+          tma_load_4d_pair(sQg, &p.tm_q, fQG, dcol, qrow, hq, bq);
+        }
+      }
+      __syncwarp();
+    }
+    // ================================================================ MMA issuer: one thread of the LEADER CTA
+    else if (warp == 12) {
+      if (rank == 0 && n_iter > 0 && elect_one()) {
+        constexpr uint32_t fmt = Elt<T>::kFmt;
+        constexpr uint32_t id_s = make_idesc(fmt, fmt, 0, 0, 256, 128);    // S^T, dP^T : K-major A and B
+        constexpr uint32_t id_dkv = make_idesc(fmt, fmt, 0, 1, 256, kD);   // dV, dK   : A in TMEM, B MN-major
+        constexpr uint32_t id_dq = make_idesc(fmt, fmt, 1, 1, 128, kD);    // dQ       : A and B MN-major
+        constexpr uint64_t dk_major = smem_desc_sw128(16, 1024);
+        constexpr uint64_t dmn_major = smem_desc_sw128(16384, 1024);
+        constexpr uint32_t hi_k = uint32_t(dk_major >> 32), hi_mn = uint32_t(dmn_major >> 32);
+        auto lo_k = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | uint32_t(dk_major); };
+        auto lo_mn = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | uint32_t(dmn_major); };
+        auto mk = [](uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; };
+        // S^T / dP^T: A = 128 x 128 K-major tile (two 16 KB d panels), B = 64 x 128 K-major (two 8 KB d panels)
+        auto mma_kmajor = [&](uint32_t d_t, uint32_t a0, uint32_t b0) {
+          const uint32_t la = lo_k(a0), lb = lo_k(b0);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t offa = ((kk / 4) * 16384 + (kk % 4) * 32) >> 4;
+            const uint32_t offb = ((kk / 4) * 8192 + (kk % 4) * 32) >> 4;
+            mma_ss_pair(d_t, mk(hi_k, la + offa), mk(hi_k, lb + offb), id_s, kk > 0);
+          }
+        };
+        auto mma_ts_mn = [&](uint32_t d_t, uint32_t a_t, uint32_t b0, bool acc) {
+          const uint32_t lb = lo_mn(b0);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ts_pair(d_t, a_t + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), id_dkv, (acc || kk > 0) ? 1u : 0u);
+        };
+        const uint32_t lo_ds = lo_mn(sDS), lo_kt = lo_mn(sKt);
+        mbar_wait(bar(F_KV), 0, 500);
+        mbar_wait(bar(F_QB), 0, 501);
+        tc_fence_after();
+        mma_kmajor(tS, sK, sQb);
+        mma_commit_pair(bar(S_F));
+        mma_commit_pair(bar(E_QB));
+        mbar_wait(bar(F_DOB), 0, 502);
+        tc_fence_after();
+        mma_kmajor(tDP, sV, sDOb);
+        mma_commit_pair(bar(DP_F));
+        mma_commit_pair(bar(E_DOB));
+        for (int it = 0; it < n_iter; ++it) {
+          const uint32_t ph = it & 1;
+          mbar_wait(bar(P_F), ph, 510);
+          mbar_wait(bar(F_DOG), ph, 515);
+          tc_fence_after();
+          mma_ts_mn(tDV, tS, sDOg, it > 0);
+          mma_commit_pair(bar(E_DOG));
+          mbar_wait(bar(DS_F), ph, 511);
+          mbar_wait(bar(F_QG), ph, 516);
+          tc_fence_after();
+          mma_ts_mn(tDK, tS + 64, sQg, it > 0);
+          mma_commit_pair(bar(E_QG));
+          mbar_wait(bar(DS_IN), ph, 517);     // dS^T rows of both key blocks have landed in my shared memory ...
+          mbar_wait(bar(DS_PEER), ph, 518);   // ... and in the peer's
+          fence_proxy_async();
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk)
+            mma_ss_pair(tDP, mk(hi_mn, lo_ds + kk * (2048 >> 4)), mk(hi_mn, lo_kt + kk * (2048 >> 4)), id_dq, kk > 0);
+          mma_commit_pair(bar(DQ_F));
+          if (it + 1 < n_iter) {
+            mbar_wait(bar(F_QB), (it + 1) & 1, 512);
+            tc_fence_after();
+            mma_kmajor(tS, sK, sQb);
+            mma_commit_pair(bar(S_F));
+            mma_commit_pair(bar(E_QB));
+            mbar_wait(bar(DQ_E), ph, 513);           // dQ_it drained out of TMEM [128,192) in both CTAs
+            mbar_wait(bar(F_DOB), (it + 1) & 1, 514);
+            tc_fence_after();
+            mma_kmajor(tDP, sV, sDOb);
+            mma_commit_pair(bar(DP_F));
+            mma_commit_pair(bar(E_DOB));
+          }
+        }
+        mma_commit_pair(bar(DKV_F));
+      }
+      if (rank == 1 && elect_one()) {
+        // relay: tell the leader when this CTA's dS^T tile (local stores + the peer's st.async) is complete
+        const uint32_t peer_bar = mapa_rank(bar(DS_PEER), 0);
+        for (int it = 0; it < n_iter; ++it) {
+          mbar_wait(bar(DS_IN), it & 1, 520);
+          fence_proxy_async();
+          mbar_arrive_cluster(peer_bar);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // ================================================================ dQ drain: 64 query rows x 128 d per CTA.
+    // TMEM layout of the M=128 pair accumulator: lane = q + 64 * (d / 64), column = d % 64.
+    reg_dealloc<Cfg::kRegsDrain>();
+    const int wq = warp & 3;
+    const int q = (wq & 1) * 32 + lane;   // query row within this CTA's half
+    const int dh = wq >> 1;               // d half held by this warp's lanes
+    const uint32_t t_dq = tDP + (uint32_t(wq * 32) << 16);
+    const bool leader = (warp == 8 && lane == 0);
+    const uint32_t dqe = mapa_rank(bar(DQ_E), 0);
+    for (int it = 0; it < n_iter; ++it) {
+      const int hq = hk * p.g + it / n_m;
+      const int m = m_min + it % n_m;
+      mbar_wait(bar(DQ_F), it & 1, 600);
+      tc_fence_after();
+      // deterministic mode: the pairs that touch (query block m, query half rank) add in ascending pair order
+      int* sem = nullptr;
+      int my_turn = 0;
+      if (p.dq_semaphore) {
+        sem = p.dq_semaphore + ((int64_t(bidb) * p.h + hq) * (p.sq_r / 128) + m) * 2 + int(rank);
+        int n_lo = 0;
+        if (p.has_left) {
+          const int x = 128 * m - 127 + shift - p.wl;
+          n_lo = x <= 0 ? 0 : (x + 127) / 128;
+        }
+        my_turn = pair - (n_lo >> 1);
+        if (leader) {
+          int cur;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cur) : "l"(sem) : "memory");
+          } while (cur != my_turn);
+        }
+      }
+      uint32_t v[64];
+      tmem_ld_x32(t_dq, v);
+      tmem_ld_x32(t_dq + 32, v + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(dqe);   // TMEM [128,192) may be overwritten by the next dP^T
+      if (leader && it > 0) tma_store_wait_read<0>();   // the previous reduce-adds have read the staging buffers
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint8_t* dst = smem_gen + Cfg::kSDQ + (2 * dh + c) * 8192 + q * 128;
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+          *reinterpret_cast<uint4*>(dst + ((x ^ (q & 7)) * 16)) =
+              make_uint4(v[c * 32 + 4 * x], v[c * 32 + 4 * x + 1], v[c * 32 + 4 * x + 2], v[c * 32 + 4 * x + 3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(2, 128);
+      if (leader) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_reduce_add_4d(&p.tm_dq64, sDQ + c * 8192, c * 32, m * 128 + 64 * int(rank), hq, bidb);
+        tma_store_commit();
+      }
+      if (sem && leader) {
+        tma_store_wait<0>();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sem), "r"(my_turn + 1) : "memory");
+      }
+    }
+    if (leader) tma_store_wait<0>();
+  } else {
+    // ================================================================ compute warps (as in fa_bwd_kernel)
+    reg_alloc<Cfg::kRegsCompute>();
+    const int wq = warp & 3, hf = warp >> 2;          // key-row quadrant, query half
+    const int r = wq * 32 + lane;                       // key row within this CTA's block
+    const int j = key0 + r;                             // key index in the sequence
+    const uint32_t lane_sel = uint32_t(wq * 32) << 16;
+    const uint32_t t_s = tS + lane_sel + hf * 64;
+    const uint32_t t_dp = tDP + lane_sel + hf * 64;
+    const uint32_t t_p = tS + lane_sel + hf * 32;
+    const uint32_t t_ds = tS + lane_sel + 64 + hf * 32;
+    const float scale_log2 = p.scale_log2;
+    const int i_lo = p.has_right ? j - shift - p.wr : -(1 << 30);
+    const int i_hi = p.has_left ? j - shift + p.wl : (1 << 30);
+    const bool key_valid = j < sk_b;
+    const uint32_t pf = mapa_rank(bar(P_F), 0), dsf = mapa_rank(bar(DS_F), 0);
+    // my dS^T row (key 128*rank + r of the pair, 64 queries of half hf) lives in the CTA that owns query half hf
+    const uint32_t ds_row_local = sDS + uint32_t(128 * int(rank) + r) * 128;
+    const uint32_t ds_row_remote = mapa_rank(ds_row_local, uint32_t(hf));
+    const uint32_t ds_in_remote = mapa_rank(bar(DS_IN), uint32_t(hf));
+    const bool ds_is_local = uint32_t(hf) == rank;
+    DropoutParams drop = p.drop;
+    if constexpr (kDropout) {
+      if (p.rng_state) {
+        const uint64_t sd = p.rng_state[0], of = p.rng_state[1];
+        drop.seed_lo = uint32_t(sd); drop.seed_hi = uint32_t(sd >> 32);
+        drop.off_lo = uint32_t(of); drop.off_hi = uint32_t(of >> 32);
+      }
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int hq = hk * p.g + it / n_m;
+      const int m = m_min + it % n_m;
+      const int st = it & 1;
+      const int q0 = m * 128 + hf * 64;
+      float slope = 0.f;
+      if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + hq] / p.scale_eff;
+      mbar_wait(bar(F_ST0 + st), (it >> 1) & 1, 700);
+      mbar_wait(bar(S_F), it & 1, 701);
+      tc_fence_after();
+      uint32_t su[64];
+      tmem_ld_x32(t_s, su);
+      tmem_ld_x32(t_s + 32, su + 32);
+      tmem_wait_ld();
+      float* s = reinterpret_cast<float*>(su);
+      const float* s_lse = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + st * 512) + hf * 64;
+      const float* s_dps = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + 1024 + st * 512) + hf * 64;
+      const float rel0 = float(q0 + shift - j);
+      if constexpr (kSoftcap) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = tanh_approx(s[c] * p.softcap_pre);
+      }
+      if (p.alibi_slopes) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = fmaf(-slope, fabsf(rel0 + float(c)), s[c]);
+      }
+      bool need_mask = key0 + 127 >= sk_b;
+      if (p.has_right) need_mask |= key0 + 127 > m * 128 + shift + p.wr;
+      if (p.has_left) need_mask |= key0 < m * 128 + 127 + shift - p.wl;
+      float pr[64];
+#pragma unroll
+      for (int c4 = 0; c4 < 64; c4 += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_lse + c4);
+        pr[c4 + 0] = ex2(fmaf(s[c4 + 0], scale_log2, -l4.x));
+        pr[c4 + 1] = ex2(fmaf(s[c4 + 1], scale_log2, -l4.y));
+        pr[c4 + 2] = ex2(fmaf(s[c4 + 2], scale_log2, -l4.z));
+        pr[c4 + 3] = ex2(fmaf(s[c4 + 3], scale_log2, -l4.w));
+      }
+      if (need_mask) {
+        const int lo = i_lo - q0, hi = i_hi - q0;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) pr[c] = (!key_valid || c < lo || c > hi) ? 0.f : pr[c];
+      }
+      uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+      if constexpr (kDropout) {
+        keep_lo = keep_hi = 0u;
+        const int sh = 8 * (j & 3);
+        const uint32_t bh = uint32_t(bidb * p.h + hq);
+#pragma unroll
+        for (int c4 = 0; c4 < 64; c4 += 4) {
+          const uint4 rr = dropout_patch(drop, uint32_t(q0 + c4) >> 2, uint32_t(j) >> 2, bh);
+          uint32_t bits = (((rr.x >> sh) & 0xffu) <= drop.thr ? 1u : 0u) | (((rr.y >> sh) & 0xffu) <= drop.thr ? 2u : 0u) |
+                          (((rr.z >> sh) & 0xffu) <= drop.thr ? 4u : 0u) | (((rr.w >> sh) & 0xffu) <= drop.thr ? 8u : 0u);
+          if (c4 < 32) keep_lo |= bits << c4;
+          else keep_hi |= bits << (c4 - 32);
+        }
+      }
+      auto kept = [&](int c) { return ((c < 32 ? keep_lo >> c : keep_hi >> (c - 32)) & 1u) != 0u; };
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          if constexpr (kDropout) pk[c / 2] = Elt<T>::pack(kept(c) ? pr[c] : 0.f, kept(c + 1) ? pr[c + 1] : 0.f);
+          else pk[c / 2] = Elt<T>::pack(pr[c], pr[c + 1]);
+        }
+        tmem_st_x32(t_p, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(pf);
+      }
+      mbar_wait(bar(DP_F), it & 1, 702);
+      tc_fence_after();
+      uint32_t dk_[32];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t du[32];
+        tmem_ld_x32(t_dp + h2 * 32, du);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c4 = 0; c4 < 32; c4 += 4) {
+          const int cc = h2 * 32 + c4;
+          const float4 d4 = *reinterpret_cast<const float4*>(s_dps + cc);
+          float g0 = __uint_as_float(du[c4 + 0]), g1 = __uint_as_float(du[c4 + 1]);
+          float g2 = __uint_as_float(du[c4 + 2]), g3 = __uint_as_float(du[c4 + 3]);
+          if constexpr (kDropout) {
+            g0 = kept(cc + 0) ? g0 * drop.rp : 0.f;
+            g1 = kept(cc + 1) ? g1 * drop.rp : 0.f;
+            g2 = kept(cc + 2) ? g2 * drop.rp : 0.f;
+            g3 = kept(cc + 3) ? g3 * drop.rp : 0.f;
+          }
+          float e0 = pr[cc + 0] * (g0 - d4.x);
+          float e1 = pr[cc + 1] * (g1 - d4.y);
+          float e2 = pr[cc + 2] * (g2 - d4.z);
+          float e3 = pr[cc + 3] * (g3 - d4.w);
+          if constexpr (kSoftcap) {
+            float t0 = s[cc + 0], t1 = s[cc + 1], t2 = s[cc + 2], t3 = s[cc + 3];
+            if (p.alibi_slopes) {
+              t0 = fmaf(slope, fabsf(rel0 + float(cc + 0)), t0);
+              t1 = fmaf(slope, fabsf(rel0 + float(cc + 1)), t1);
+              t2 = fmaf(slope, fabsf(rel0 + float(cc + 2)), t2);
+              t3 = fmaf(slope, fabsf(rel0 + float(cc + 3)), t3);
+            }
+            e0 *= 1.f - t0 * t0;
+            e1 *= 1.f - t1 * t1;
+            e2 *= 1.f - t2 * t2;
+            e3 *= 1.f - t3 * t3;
+          }
+          dk_[cc / 2] = Elt<T>::pack(e0, e1);
+          dk_[cc / 2 + 1] = Elt<T>::pack(e2, e3);
+        }
+      }
+      tmem_st_x32(t_ds, dk_);
+      // shared copy for dQ = dS K: 128-byte row (64 queries of half hf) of key 128*rank + r, 16-byte chunks XOR-swizzled,
+      // written into the CTA that owns query half hf (the peer through distributed shared memory)
+      if (ds_is_local) {
+        uint8_t* dst = smem_gen + Cfg::kSDS + (128 * int(rank) + r) * 128;
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+          *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) =
+              make_uint4(dk_[4 * x], dk_[4 * x + 1], dk_[4 * x + 2], dk_[4 * x + 3]);
+      } else {
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+          st_async_v4(ds_row_remote + uint32_t((x ^ (r & 7)) * 16),
+                      make_uint4(dk_[4 * x], dk_[4 * x + 1], dk_[4 * x + 2], dk_[4 * x + 3]), ds_in_remote);
+      }
+      tmem_wait_st();
+      if (ds_is_local) fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (ds_is_local) {   // shared-memory half of the hand-off: 4 local writer warps + the peer's 16 KB of st.async
+          if (wq == 0) mbar_arrive_expect_tx(bar(DS_IN), 16384);
+          else mbar_arrive(bar(DS_IN));
+        }
+        mbar_arrive_cluster(dsf);   // TMEM half (dS^T for dK): all 16 compute warps of the pair
+      }
+    }
+    // ---------------------------------------------------------------- epilogue: dK (x scale), dV (x 1/p_keep)
+    if (n_iter > 0) {
+      mbar_wait(bar(DKV_F), 0, 710);
+      tc_fence_after();
+    }
+    const int bk = p.cu_seqlens_k ? 0 : bidb;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t t_src = (which == 0 ? tDV : tDK) + lane_sel;
+      const float mul = which == 0 ? (kDropout ? drop.rp : 1.0f) : p.scale;
+      T* base = reinterpret_cast<T*>(which == 0 ? p.dv : p.dk) +
+                int64_t(bk) * (which == 0 ? p.dv_batch_stride : p.dk_batch_stride) +
+                int64_t(k_off + j) * (which == 0 ? p.dv_row_stride : p.dk_row_stride) +
+                int64_t(hk) * (which == 0 ? p.dv_head_stride : p.dk_head_stride);
+      constexpr int kHalf = kD / 2;
+#pragma unroll
+      for (int cc = 0; cc < kHalf; cc += 32) {
+        uint32_t o[32];
+        if (n_iter > 0) {
+          tmem_ld_x32(t_src + hf * kHalf + cc, o);
+          tmem_wait_ld();
+        }
+        if (key_valid) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            const int col = hf * kHalf + cc + c;
+            if (col < p.d) {
+              uint4 v4 = make_uint4(0, 0, 0, 0);
+              if (n_iter > 0) {
+                v4.x = Elt<T>::pack(__uint_as_float(o[c]) * mul, __uint_as_float(o[c + 1]) * mul);
+                v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * mul, __uint_as_float(o[c + 3]) * mul);
+                v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * mul, __uint_as_float(o[c + 5]) * mul);
+                v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * mul, __uint_as_float(o[c + 7]) * mul);
+              }
+              *reinterpret_cast<uint4*>(base + col) = v4;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves while the peer may still signal its barriers or write its shared memory
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace fa

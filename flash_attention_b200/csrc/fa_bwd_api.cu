@@ -9,6 +9,7 @@
 
 #include "../../include/fa_b200.h"
 #include "fa_api_common.h"
+#include "fa_bwd2_sm100.cuh"
 #include "fa_bwd_sm100.cuh"
 
 namespace fa {
@@ -46,7 +47,8 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   pl->off_dps = align256(stat);
   pl->off_dq = pl->off_dps + align256(stat);
   pl->off_sem = pl->off_dq + align256(stat * pl->kD);   // deterministic mode: one counter per (b, h, query block),
-  pl->total = pl->off_sem + align256(stat / 128);        // placed right behind dq_accum so one memset clears both
+  pl->total = pl->off_sem + align256(stat / 128 * 2);    // placed right behind dq_accum so one memset clears both
+                                                          // (x2: the CTA-pair kernel orders each query half separately)
   return 0;
 }
 
@@ -65,6 +67,29 @@ static int launch_bwd_main(const BwdKernelParams& kp, dim3 grid, cudaStream_t st
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("fa_bwd_kernel launch: ") + cudaGetErrorString(e));
   return 0;
+}
+
+// CTA-pair main loop (fa_bwd2_sm100.cuh): head dim 128 only
+template <typename T, bool kSoftcap, bool kDropout>
+static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = fa_bwd2_kernel<T, kSoftcap, kDropout>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(bwd2): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  grid.x = (grid.x + 1) / 2 * 2;  // whole pairs (compile-time cluster dims (2,1,1))
+  kern<<<grid, Bwd2Cfg::kThreads, Bwd2Cfg::kSmemBytes, stream>>>(kp);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_bwd2_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+static bool use_pair_kernel(int kD) {
+  static int mode = [] { const char* e = getenv("FA_B200_BWD_PAIR"); return e ? atoi(e) : 0; }();
+  return kD == 128 && mode != 0;
 }
 
 template <typename T, int kD>
@@ -109,6 +134,24 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
     if (int rc = make_tmap(&kp.tm_dq, FA_BWD_DQ_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                            dq_accum, dims, str, box)) return rc;
   }
+  const bool pair = use_pair_kernel(kD);
+  if (pair) {
+    auto map64 = [&](CUtensorMap* tm, const void* base, int64_t bs, int64_t rs, int64_t hs, int rows_dense, int rows_varlen,
+                     int heads) -> int {
+      uint64_t rows = varlen ? rows_varlen : rows_dense, nb = varlen ? 1 : a.b;
+      uint64_t dims[4] = {uint64_t(a.d), rows, uint64_t(heads), nb};
+      uint64_t str[3] = {uint64_t(rs) * 2, uint64_t(hs) * 2, uint64_t(bs) * 2};
+      if (nb == 1) str[2] = rows * str[0];
+      uint32_t box[4] = {64, 64, 1, 1};
+      return make_tmap(tm, dt, 4, base, dims, str, box);
+    };
+    if (int rc = map64(&kp.tm_q64, a.q, a.q_batch_stride, a.q_row_stride, a.q_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
+    if (int rc = map64(&kp.tm_do64, a.dout, a.do_batch_stride, a.do_row_stride, a.do_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
+    uint64_t dims[4] = {uint64_t(kD), uint64_t(sq_r), uint64_t(a.h), uint64_t(a.b)};
+    uint64_t str[3] = {uint64_t(kD) * 4, uint64_t(sq_r) * kD * 4, uint64_t(a.h) * sq_r * kD * 4};
+    uint32_t box[4] = {32, 64, 1, 1};
+    if (int rc = make_tmap(&kp.tm_dq64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, dims, str, box)) return rc;
+  }
   kp.lse_log2 = lse_log2;
   kp.dq_semaphore = a.deterministic ? reinterpret_cast<int*>(ws + pl.off_sem) : nullptr;
   kp.dpsum = dpsum;
@@ -125,13 +168,23 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   else { kp.softcap_pre = 0.f; kp.scale_eff = a.softmax_scale; }
   kp.scale_log2 = kp.scale_eff * float(M_LOG2E);
   dim3 grid((a.seqlen_k + 127) / 128, a.h_k, a.b);
-  int rc;
+  int rc = 0;
+  bool launched = false;
   if (a.p_dropout > 0.f) {
     kp.drop = make_dropout_params(a.p_dropout, a.philox_seed, a.philox_offset);
     kp.rng_state = a.rng_state;
-    rc = launch_bwd_main<T, kD, false, true>(kp, grid, stream);
-  } else {
-    rc = a.softcap > 0.f ? launch_bwd_main<T, kD, true>(kp, grid, stream) : launch_bwd_main<T, kD, false>(kp, grid, stream);
+  }
+  if constexpr (kD == 128) {
+    if (pair) {
+      rc = a.p_dropout > 0.f ? launch_bwd_pair<T, false, true>(kp, grid, stream)
+         : a.softcap > 0.f ? launch_bwd_pair<T, true, false>(kp, grid, stream)
+                           : launch_bwd_pair<T, false, false>(kp, grid, stream);
+      launched = true;
+    }
+  }
+  if (!launched) {
+    if (a.p_dropout > 0.f) rc = launch_bwd_main<T, kD, false, true>(kp, grid, stream);
+    else rc = a.softcap > 0.f ? launch_bwd_main<T, kD, true>(kp, grid, stream) : launch_bwd_main<T, kD, false>(kp, grid, stream);
   }
   if (rc) return rc;
   {
