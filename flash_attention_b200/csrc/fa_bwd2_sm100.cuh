@@ -24,6 +24,27 @@
 
 namespace fa {
 
+#ifndef FA_BWD2_POLY
+#define FA_BWD2_POLY 0   // n > 0: of every n groups of 4 scores, one group computes 2 of its exp2 on the FMA pipe
+#endif
+
+#ifndef FA_BWD2_LOCAL_DS
+#define FA_BWD2_LOCAL_DS 0   // 1: TIMING EXPERIMENT ONLY (wrong dQ): every warp stores its dS^T rows into its own CTA
+#endif
+#ifndef FA_BWD2_TS
+#define FA_BWD2_TS 0     // 1: CTA pair (0,0,0) records clock64 stamps of its pipeline events (timeline debugging build)
+#endif
+#if FA_BWD2_TS
+__device__ unsigned long long g_bwd2_ts[2 * 16 * 32];   // [rank][iteration - 8][event]
+#define TS(ev)                                                                                          \
+  do {                                                                                                  \
+    if (blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && it >= 8 && it < 24)                      \
+      g_bwd2_ts[(int(rank) * 16 + (it - 8)) * 32 + (ev)] = clock64();                                    \
+  } while (0)
+#else
+#define TS(ev) do {} while (0)
+#endif
+
 struct Bwd2Cfg {
   static constexpr int kThreads = 512;
   static constexpr int kRegsCompute = 160, kRegsDrain = 96, kRegsOther = 96;
@@ -35,10 +56,11 @@ struct Bwd2Cfg {
   static constexpr int kSDOb = kSQg + 16384;     // dO[query half r, all d]                    K-major B of dP^T
   static constexpr int kSDOg = kSDOb + 16384;    // dO[128 queries, d half r]                  MN-major B of dV
   static constexpr int kSDS = kSDOg + 16384;     // dS^T[256 pair keys, query half r]          MN-major A of dQ
-  static constexpr int kSDQ = kSDS + 32768;      // dQ staging: 4 chunks of 64 rows x 32 fp32
-  static constexpr int kSStat = kSDQ + 32768;    // lse_log2[2][128], dpsum[2][128]
+  static constexpr int kSDQ = kSDS + 32768;      // dQ staging: 2 chunks of 64 rows x 32 fp32 (two rounds per tile)
+  static constexpr int kSDX = kSDQ + 16384;      // export staging: the dS^T rows owed to the peer (128 keys x 64 queries)
+  static constexpr int kSStat = kSDX + 16384;    // lse_log2[2][128], dpsum[2][128]
   static constexpr int kSBar = kSStat + 2048;
-  static constexpr int kNumBars = 20;
+  static constexpr int kNumBars = 26;
   static constexpr int kSmemBytes = kSBar + 8 * kNumBars + 16;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -82,12 +104,12 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   const uint32_t sK = smem_base + Cfg::kSK, sV = smem_base + Cfg::kSV, sKt = smem_base + Cfg::kSKt;
   const uint32_t sQb = smem_base + Cfg::kSQb, sQg = smem_base + Cfg::kSQg;
   const uint32_t sDOb = smem_base + Cfg::kSDOb, sDOg = smem_base + Cfg::kSDOg;
-  const uint32_t sDS = smem_base + Cfg::kSDS, sDQ = smem_base + Cfg::kSDQ;
+  const uint32_t sDS = smem_base + Cfg::kSDS, sDQ = smem_base + Cfg::kSDQ, sDX = smem_base + Cfg::kSDX;
   const uint32_t sStat = smem_base + Cfg::kSStat, sBar = smem_base + Cfg::kSBar;
   // F_*: "operand landed" barriers, live in the LEADER (rank 0) and collect the TMA bytes of both CTAs
   // E_*: "operand consumed" barriers, one per CTA, signalled by multicast tcgen05.commit
   enum { F_KV = 0, F_QB = 1, F_DOB = 2, F_DOG = 3, F_QG = 4, E_QB = 5, E_DOB = 6, E_DOG = 7, E_QG = 8, F_ST0 = 9,
-         F_ST1 = 10, S_F = 11, DP_F = 12, P_F = 13, DS_F = 14, DQ_F = 15, DQ_E = 16, DKV_F = 17, DS_IN = 18, DS_PEER = 19 };
+         F_ST1 = 10, S_F = 11, DP_F = 12, P_F = 13, DS_F = 14, DQ_F = 15, DQ_E = 16, DKV_F = 17, DS_IN = 18, DS_PEER = 19, T_DV = 20, T_S = 21, T_DK = 22, T_DQ = 23, T_DP = 24, S_RD = 25 };
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSBar + 8 * Cfg::kNumBars);
@@ -107,7 +129,11 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       mbar_init(bar(P_F), 16); mbar_init(bar(DS_F), 16);   // 8 compute warps of each CTA
       mbar_init(bar(DQ_F), 1); mbar_init(bar(DQ_E), 8);    // 4 drain warps of each CTA
       mbar_init(bar(DKV_F), 1);
-      mbar_init(bar(DS_IN), 4);     // the 4 local writer warps of sDS (+ 16 KB of st.async tx-bytes from the peer)
+      mbar_init(bar(DS_IN), FA_BWD2_LOCAL_DS ? 8 : 4);     // the 4 local writer warps of sDS (+ 16 KB of st.async tx-bytes from the peer)
+#if FA_BWD2_TS
+      mbar_init(bar(T_DV), 1); mbar_init(bar(T_S), 1); mbar_init(bar(T_DK), 1); mbar_init(bar(T_DQ), 1); mbar_init(bar(T_DP), 1);
+#endif
+      mbar_init(bar(S_RD), 16);     // leader only: all compute warps of the pair have read S^T out of TMEM
       mbar_init(bar(DS_PEER), 1);   // leader only: the peer's sDS is complete (relayed by the peer's warp 12)
       fence_barrier_init();
     }
@@ -166,6 +192,20 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       }
       __syncwarp();
     }
+#if FA_BWD2_TS
+    else if (warp == 14) {
+      if (rank == 0 && lane == 0) {   // completion times of the MMA groups (leader clock)
+        for (int it = 0; it < n_iter; ++it) {
+          mbar_wait(bar(T_DV), it & 1, 800); TS(21);
+          if (it + 1 < n_iter) { mbar_wait(bar(T_S), it & 1, 801); TS(22); }
+          mbar_wait(bar(T_DK), it & 1, 802); TS(23);
+          mbar_wait(bar(T_DQ), it & 1, 803); TS(24);
+          if (it + 1 < n_iter) { mbar_wait(bar(T_DP), it & 1, 804); TS(25); }
+        }
+      }
+      __syncwarp();
+    }
+#endif
     // ================================================================ MMA issuer: one thread of the LEADER CTA
     else if (warp == 12) {
       if (rank == 0 && n_iter > 0 && elect_one()) {
@@ -207,39 +247,75 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         mma_kmajor(tDP, sV, sDOb);
         mma_commit_pair(bar(DP_F));
         mma_commit_pair(bar(E_DOB));
+        // TMEM regions and their tenants over one tile n (accumulators dV [256,384) and dK [384,512) aside):
+        //   R1 = [0,128)   : S^T(n) fp32 -> once read: P^T(n) packed in [0,64), dQ(n-1 .. see below) in [64,128)
+        //   R2 = [128,256) : dP^T(n) fp32 -> once read: dS^T(n) packed in [128,192)
+        // Issue order dV(n), S^T(n+1), dK(n), dP^T(n+1), dQ(n): every MMA only waits for its own inputs; S^T(n+1) runs
+        // while the compute warps still form dS^T(n), dP^T(n+1) right behind dK(n) while they form P^T(n+1), and dQ(n)
+        // -- which has to wait for the exported half of dS^T -- lands in R1[64,128) after S^T(n+1) has been read, off the
+        // critical path (it only has to be drained before S^T(n+2) is issued).
         for (int it = 0; it < n_iter; ++it) {
           const uint32_t ph = it & 1;
+          const bool more = it + 1 < n_iter;
           mbar_wait(bar(P_F), ph, 510);
+          TS(0);
+          mbar_wait(bar(S_RD), ph, 521);   // (already complete: every warp reads S^T before it delivers P^T; keeps the phases in step)
           mbar_wait(bar(F_DOG), ph, 515);
           tc_fence_after();
           mma_ts_mn(tDV, tS, sDOg, it > 0);
           mma_commit_pair(bar(E_DOG));
-          mbar_wait(bar(DS_F), ph, 511);
-          mbar_wait(bar(F_QG), ph, 516);
-          tc_fence_after();
-          mma_ts_mn(tDK, tS + 64, sQg, it > 0);
-          mma_commit_pair(bar(E_QG));
-          mbar_wait(bar(DS_IN), ph, 517);     // dS^T rows of both key blocks have landed in my shared memory ...
-          mbar_wait(bar(DS_PEER), ph, 518);   // ... and in the peer's
-          fence_proxy_async();
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < 16; ++kk)
-            mma_ss_pair(tDP, mk(hi_mn, lo_ds + kk * (2048 >> 4)), mk(hi_mn, lo_kt + kk * (2048 >> 4)), id_dq, kk > 0);
-          mma_commit_pair(bar(DQ_F));
-          if (it + 1 < n_iter) {
+#if FA_BWD2_TS
+          mma_commit_pair(bar(T_DV));
+#endif
+          TS(1);
+          if (more) {
+            if (it > 0) mbar_wait(bar(DQ_E), ph ^ 1, 513);   // dQ(it-1) drained out of R1[64,128) in both CTAs
+            TS(6);
             mbar_wait(bar(F_QB), (it + 1) & 1, 512);
+            TS(2);
             tc_fence_after();
             mma_kmajor(tS, sK, sQb);
             mma_commit_pair(bar(S_F));
             mma_commit_pair(bar(E_QB));
-            mbar_wait(bar(DQ_E), ph, 513);           // dQ_it drained out of TMEM [128,192) in both CTAs
+#if FA_BWD2_TS
+            mma_commit_pair(bar(T_S));
+#endif
+          }
+          mbar_wait(bar(DS_F), ph, 511);
+          TS(3);
+          mbar_wait(bar(F_QG), ph, 516);
+          tc_fence_after();
+          mma_ts_mn(tDK, tDP, sQg, it > 0);
+          mma_commit_pair(bar(E_QG));
+#if FA_BWD2_TS
+          mma_commit_pair(bar(T_DK));
+#endif
+          if (more) {
             mbar_wait(bar(F_DOB), (it + 1) & 1, 514);
             tc_fence_after();
             mma_kmajor(tDP, sV, sDOb);
             mma_commit_pair(bar(DP_F));
             mma_commit_pair(bar(E_DOB));
+#if FA_BWD2_TS
+            mma_commit_pair(bar(T_DP));
+#endif
+            TS(7);
           }
+          mbar_wait(bar(DS_IN), ph, 517);     // dS^T rows of both key blocks have landed in my shared memory ...
+          TS(4);
+          mbar_wait(bar(DS_PEER), ph, 518);   // ... and in the peer's
+          TS(5);
+          if (more) mbar_wait(bar(S_RD), (it + 1) & 1, 519);   // S^T(it+1) is out of R1: its upper half is free for dQ
+          else if (it > 0) mbar_wait(bar(DQ_E), ph ^ 1, 522);  // last tile: no S^T issue waited for the previous dQ's drain
+          fence_proxy_async();
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk)
+            mma_ss_pair(tS + 64, mk(hi_mn, lo_ds + kk * (2048 >> 4)), mk(hi_mn, lo_kt + kk * (2048 >> 4)), id_dq, kk > 0);
+          mma_commit_pair(bar(DQ_F));
+#if FA_BWD2_TS
+          mma_commit_pair(bar(T_DQ));
+#endif
         }
         mma_commit_pair(bar(DKV_F));
       }
@@ -261,13 +337,14 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     const int wq = warp & 3;
     const int q = (wq & 1) * 32 + lane;   // query row within this CTA's half
     const int dh = wq >> 1;               // d half held by this warp's lanes
-    const uint32_t t_dq = tDP + (uint32_t(wq * 32) << 16);
+    const uint32_t t_dq = tS + 64 + (uint32_t(wq * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
     const uint32_t dqe = mapa_rank(bar(DQ_E), 0);
     for (int it = 0; it < n_iter; ++it) {
       const int hq = hk * p.g + it / n_m;
       const int m = m_min + it % n_m;
       mbar_wait(bar(DQ_F), it & 1, 600);
+      if (warp == 8 && lane == 0) TS(12);
       tc_fence_after();
       // deterministic mode: the pairs that touch (query block m, query half rank) add in ascending pair order
       int* sem = nullptr;
@@ -293,24 +370,24 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(dqe);   // TMEM [128,192) may be overwritten by the next dP^T
-      if (leader && it > 0) tma_store_wait_read<0>();   // the previous reduce-adds have read the staging buffers
-      named_bar_sync(1, 128);
+      if (lane == 0) mbar_arrive_cluster(dqe);   // TMEM [64,128) may be overwritten by the S^T after next
+      if (warp == 8 && lane == 0) TS(13);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint8_t* dst = smem_gen + Cfg::kSDQ + (2 * dh + c) * 8192 + q * 128;
+      for (int c = 0; c < 2; ++c) {   // two rounds: 32-column chunk c of each d half
+        if (leader && (it > 0 || c > 0)) tma_store_wait_read<0>();   // the previous reduce-adds have read the staging
+        named_bar_sync(1, 128);
+        uint8_t* dst = smem_gen + Cfg::kSDQ + dh * 8192 + q * 128;
 #pragma unroll
         for (int x = 0; x < 8; ++x)
           *reinterpret_cast<uint4*>(dst + ((x ^ (q & 7)) * 16)) =
               make_uint4(v[c * 32 + 4 * x], v[c * 32 + 4 * x + 1], v[c * 32 + 4 * x + 2], v[c * 32 + 4 * x + 3]);
-      }
-      fence_proxy_async();
-      named_bar_sync(2, 128);
-      if (leader) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tma_reduce_add_4d(&p.tm_dq64, sDQ + c * 8192, c * 32, m * 128 + 64 * int(rank), hq, bidb);
-        tma_store_commit();
+        fence_proxy_async();
+        named_bar_sync(2, 128);
+        if (leader) {
+          tma_reduce_add_4d(&p.tm_dq64, sDQ, c * 32, m * 128 + 64 * int(rank), hq, bidb);
+          tma_reduce_add_4d(&p.tm_dq64, sDQ + 8192, 64 + c * 32, m * 128 + 64 * int(rank), hq, bidb);
+          tma_store_commit();
+        }
       }
       if (sem && leader) {
         tma_store_wait<0>();
@@ -330,17 +407,17 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     const uint32_t t_s = tS + lane_sel + hf * 64;
     const uint32_t t_dp = tDP + lane_sel + hf * 64;
     const uint32_t t_p = tS + lane_sel + hf * 32;
-    const uint32_t t_ds = tS + lane_sel + 64 + hf * 32;
+    const uint32_t t_ds = tDP + lane_sel + hf * 32;   // dS^T packed: over the dP^T columns [0,64) once both halves are read
     const float scale_log2 = p.scale_log2;
     const int i_lo = p.has_right ? j - shift - p.wr : -(1 << 30);
     const int i_hi = p.has_left ? j - shift + p.wl : (1 << 30);
     const bool key_valid = j < sk_b;
-    const uint32_t pf = mapa_rank(bar(P_F), 0), dsf = mapa_rank(bar(DS_F), 0);
+    const uint32_t pf = mapa_rank(bar(P_F), 0), dsf = mapa_rank(bar(DS_F), 0), srd = mapa_rank(bar(S_RD), 0);
     // my dS^T row (key 128*rank + r of the pair, 64 queries of half hf) lives in the CTA that owns query half hf
-    const uint32_t ds_row_local = sDS + uint32_t(128 * int(rank) + r) * 128;
-    const uint32_t ds_row_remote = mapa_rank(ds_row_local, uint32_t(hf));
+    // exporter warps stage their 32 rows (4 KB) locally and ship them with one bulk copy into the peer's sDS
+    const uint32_t ds_warp_remote = mapa_rank(sDS + uint32_t(128 * int(rank) + wq * 32) * 128, uint32_t(hf));
     const uint32_t ds_in_remote = mapa_rank(bar(DS_IN), uint32_t(hf));
-    const bool ds_is_local = uint32_t(hf) == rank;
+    const bool ds_is_local = FA_BWD2_LOCAL_DS ? true : uint32_t(hf) == rank;
     DropoutParams drop = p.drop;
     if constexpr (kDropout) {
       if (p.rng_state) {
@@ -358,11 +435,15 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + hq] / p.scale_eff;
       mbar_wait(bar(F_ST0 + st), (it >> 1) & 1, 700);
       mbar_wait(bar(S_F), it & 1, 701);
+      if (warp == 0 && lane == 0) TS(8);
       tc_fence_after();
       uint32_t su[64];
       tmem_ld_x32(t_s, su);
       tmem_ld_x32(t_s + 32, su + 32);
       tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(srd);   // my S^T columns are in registers
       float* s = reinterpret_cast<float*>(su);
       const float* s_lse = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + st * 512) + hf * 64;
       const float* s_dps = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + 1024 + st * 512) + hf * 64;
@@ -384,8 +465,12 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         const float4 l4 = *reinterpret_cast<const float4*>(s_lse + c4);
         pr[c4 + 0] = ex2(fmaf(s[c4 + 0], scale_log2, -l4.x));
         pr[c4 + 1] = ex2(fmaf(s[c4 + 1], scale_log2, -l4.y));
-        pr[c4 + 2] = ex2(fmaf(s[c4 + 2], scale_log2, -l4.z));
-        pr[c4 + 3] = ex2(fmaf(s[c4 + 3], scale_log2, -l4.w));
+        if (FA_BWD2_POLY && ((c4 >> 2) % FA_BWD2_POLY) == 0) {  // FMA-pipe exp2 for a share of the elements (MUFU relief)
+          ex2_poly2(fmaf(s[c4 + 2], scale_log2, -l4.z), fmaf(s[c4 + 3], scale_log2, -l4.w), pr[c4 + 2], pr[c4 + 3]);
+        } else {
+          pr[c4 + 2] = ex2(fmaf(s[c4 + 2], scale_log2, -l4.z));
+          pr[c4 + 3] = ex2(fmaf(s[c4 + 3], scale_log2, -l4.w));
+        }
       }
       if (need_mask) {
         const int lo = i_lo - q0, hi = i_hi - q0;
@@ -419,8 +504,10 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(pf);
+        if (warp == 0 && lane == 0) TS(9);
       }
       mbar_wait(bar(DP_F), it & 1, 702);
+      if (warp == 0 && lane == 0) TS(10);
       tc_fence_after();
       uint32_t dk_[32];
 #pragma unroll
@@ -461,32 +548,44 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
           dk_[cc / 2 + 1] = Elt<T>::pack(e2, e3);
         }
       }
+      if (warp == 0 && lane == 0) TS(14);
+      if (warp == 4 && lane == 0) TS(18);
+      named_bar_sync(3 + wq, 64);   // the other query-half warp of this lane quadrant has read its dP^T columns too
+      if (warp == 0 && lane == 0) TS(16);
+      if (warp == 4 && lane == 0) TS(19);
       tmem_st_x32(t_ds, dk_);
+      if (warp == 0 && lane == 0) TS(26);
       // shared copy for dQ = dS K: 128-byte row (64 queries of half hf) of key 128*rank + r, 16-byte chunks XOR-swizzled,
       // written into the CTA that owns query half hf (the peer through distributed shared memory)
-      if (ds_is_local) {
-        uint8_t* dst = smem_gen + Cfg::kSDS + (128 * int(rank) + r) * 128;
+      // dQ of the previous tile (issued BEHIND this tile's dP^T) must have finished reading sDS in both CTAs before
+      // anyone overwrites it (locally or with a bulk copy into the peer)
+      if (it > 0) mbar_wait(bar(DQ_F), (it - 1) & 1, 703);
+      {
+        uint8_t* dst = ds_is_local ? smem_gen + Cfg::kSDS + (128 * int(rank) + r) * 128 : smem_gen + Cfg::kSDX + r * 128;
 #pragma unroll
         for (int x = 0; x < 8; ++x)
           *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) =
               make_uint4(dk_[4 * x], dk_[4 * x + 1], dk_[4 * x + 2], dk_[4 * x + 3]);
-      } else {
-#pragma unroll
-        for (int x = 0; x < 8; ++x)
-          st_async_v4(ds_row_remote + uint32_t((x ^ (r & 7)) * 16),
-                      make_uint4(dk_[4 * x], dk_[4 * x + 1], dk_[4 * x + 2], dk_[4 * x + 3]), ds_in_remote);
       }
-      tmem_wait_st();
-      if (ds_is_local) fence_proxy_async();
-      tc_fence_before();
+      if (warp == 0 && lane == 0) TS(17);
+      // shared-memory half of the hand-off first (the export has the longest way to go), then the TMEM half
+      fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        if (ds_is_local) {   // shared-memory half of the hand-off: 4 local writer warps + the peer's 16 KB of st.async
-          if (wq == 0) mbar_arrive_expect_tx(bar(DS_IN), 16384);
+        if (ds_is_local) {   // 4 local writer warps + 16 KB of bulk copies from the peer complete DS_IN
+          if (wq == 0 && !FA_BWD2_LOCAL_DS) mbar_arrive_expect_tx(bar(DS_IN), 16384);
           else mbar_arrive(bar(DS_IN));
+        } else {
+          bulk_copy_to_cluster(ds_warp_remote, sDX + uint32_t(wq * 32) * 128, 4096, ds_in_remote);
         }
-        mbar_arrive_cluster(dsf);   // TMEM half (dS^T for dK): all 16 compute warps of the pair
       }
+      tmem_wait_st();
+      if (warp == 0 && lane == 0) TS(15);
+      if (warp == 4 && lane == 0) TS(20);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(dsf);   // TMEM half (dS^T for dK): all 16 compute warps of the pair
+      if (warp == 0 && lane == 0) TS(11);
     }
     // ---------------------------------------------------------------- epilogue: dK (x scale), dV (x 1/p_keep)
     if (n_iter > 0) {

@@ -88,7 +88,8 @@ static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t st
 }
 
 static bool use_pair_kernel(int kD) {
-  static int mode = [] { const char* e = getenv("FA_B200_BWD_PAIR"); return e ? atoi(e) : 0; }();
+  // default on: measured 1125-1239 vs 1000-1084 TFLOP/s (bwd, b4 h16 s8192 d128); FA_B200_BWD_PAIR=0 selects fa_bwd_kernel
+  static int mode = [] { const char* e = getenv("FA_B200_BWD_PAIR"); return e ? atoi(e) : 1; }();
   return kD == 128 && mode != 0;
 }
 
@@ -223,6 +224,12 @@ int fa_b200_mha_varlen_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream
   if (!args) return set_error("null args");
   return run_bwd(*args, true, static_cast<cudaStream_t>(stream));
 }
+#if FA_BWD2_TS
+// timeline-debugging builds only (not declared in include/fa_b200.h): copies the clock64 stamps of the pair kernel
+int fa_b200_debug_read_ts(unsigned long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, fa::g_bwd2_ts, size_t(n) * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
 size_t fa_b200_bwd_workspace_bytes(const fa_b200_bwd_args* args) {
   BwdPlan pl;
   if (!args || plan_bwd(*args, args->cu_seqlens_q != nullptr, &pl)) return 0;
