@@ -233,7 +233,7 @@ def main():
     if mode == "fwd_bwd":
         dq, dk, dv = torch.empty_like(qd), torch.empty_like(kd), torch.empty_like(vd)
         kern = lambda: op.bwd(do, qd, kd, vd, out, lse, dq, dk, dv, None, 0.0, scale, causal, -1, -1, 0.0, False, None, None)
-        kern_flops, kern_name = flops(b, h, s, d, causal, "bwd"), "fa_bwd (preprocess + dQ/dK/dV main loop + dQ convert)"
+        kern_flops, kern_name = flops(b, h, s, d, causal, "bwd"), "fa_bwd (preprocess + CTA-pair dQ/dK/dV main loop fa_bwd2_kernel + dQ convert)"
     else:
         kern = lambda: op.fwd(qd, kd, vd, out, None, 0.0, scale, causal, -1, -1, 0.0, False, None)
         kern_flops, kern_name = flops(b, h, s, d, causal, "fwd"), "fa_fwd_kernel"
