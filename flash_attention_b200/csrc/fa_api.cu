@@ -339,6 +339,11 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     kp.lse_accum = kp.o_accum + rows * pl.kD;
   }
   dim3 grid(pl.num_m_blocks, a.h / gp, a.b * pl.num_splits);
+  // masked work is uneven across m-blocks: dispatch every head's heavy m-blocks first (m-block = slowest grid dimension)
+  if (sched_lpt(pl.has_left || pl.has_right) && grid.x <= 65535 && grid.z <= 65535) {
+    kp.sched_lpt = 1;
+    grid = dim3(a.h / gp, a.b * pl.num_splits, pl.num_m_blocks);
+  }
   int rc;
   if (fp8) {
     rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream, pl.tiles);

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 namespace fa {
@@ -16,6 +17,13 @@ int set_error(const std::string& msg);
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 int num_sms();
+// Work-major (longest-first) block order, opt-in with FA_B200_SCHED=1 (=2: masked problems only).  Measured slower
+// than the head-major default on B200 (causal bwd 1024 -> 916, causal fwd 1083 -> 1028, non-causal bwd 1179 -> 948
+// TFLOP/s): CTAs of one head that run together share Q/dO (bwd) or K/V (fwd) through L2, which matters more than the tail.
+inline bool sched_lpt(bool masked) {
+  static int mode = [] { const char* e = getenv("FA_B200_SCHED"); return e ? atoi(e) : 0; }();
+  return mode == 1 || (mode == 2 && masked);
+}
 }  // namespace fa
 
 #include "fa_dropout.cuh"

@@ -38,7 +38,7 @@ namespace fa {
 __device__ unsigned long long g_bwd2_ts[2 * 16 * 32];   // [rank][iteration - 8][event]
 #define TS(ev)                                                                                          \
   do {                                                                                                  \
-    if (blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && it >= 8 && it < 24)                      \
+    if (pair == 0 && hk == 0 && bidb == 0 && it >= 8 && it < 24)                      \
       g_bwd2_ts[(int(rank) * 16 + (it - 8)) * 32 + (ev)] = clock64();                                    \
   } while (0)
 #else
@@ -71,7 +71,9 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   using Cfg = Bwd2Cfg;
   constexpr int kD = 128;
   const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, hk = blockIdx.y, bidb = blockIdx.z;
+  // grid (2 * pairs, h_k, b), or with sched_lpt (2, h_k * b, pairs): pair index slowest = heavy (masked) pairs first
+  const int pair = p.sched_lpt ? blockIdx.z : blockIdx.x >> 1;
+  const int hk = p.sched_lpt ? blockIdx.y % p.h_k : blockIdx.y, bidb = p.sched_lpt ? blockIdx.y / p.h_k : blockIdx.z;
   int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
   if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
   if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }

@@ -53,6 +53,7 @@ struct BwdKernelParams {
   float scale_eff;           // scale of the logits inside exp: softcap if softcap > 0 else softmax_scale
   float scale_log2;          // scale_eff * log2(e)
   float softcap_pre;
+  int sched_lpt;              // key block (pair) index is the slowest grid dimension: heavy (masked) work first
   DropoutParams drop;         // kDropout kernels only: the forward's rng_state and p_dropout
   const uint64_t* rng_state;  // device copy of {seed, offset}; overrides drop.seed/off when non-null
 };
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(BwdCfg<kD>::kThreads, 1)
 fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
   using Cfg = BwdCfg<kD>;
   constexpr float kNegInf = -INFINITY;
-  const int n_block = blockIdx.x, hk = blockIdx.y, bidb = blockIdx.z;
+  const int n_block = p.sched_lpt ? blockIdx.z : blockIdx.x;
+  const int hk = p.sched_lpt ? blockIdx.x : blockIdx.y, bidb = p.sched_lpt ? blockIdx.y : blockIdx.z;
   int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
   if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
   if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }

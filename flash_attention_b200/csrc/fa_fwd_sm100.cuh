@@ -59,6 +59,8 @@ struct FwdKernelParams {
   int has_right, has_left;  // window limits active (causal => has_right, wr = 0)
   int wl, wr;
   int reverse_m;            // schedule heavy m-blocks first (causal)
+  int sched_lpt;            // grid = (head slots, batch x splits, m blocks): the m-block index is the SLOWEST grid dimension,
+                            // so with a mask all heads' heaviest m-blocks are dispatched first (longest-processing-time-first)
   float scale;              // effective softmax scale (softcap if softcap > 0)
   float scale_log2;         // scale * log2(e)
   float softcap_pre;        // softmax_scale / softcap, 0 = off
@@ -134,11 +136,13 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   constexpr int kPolyPairs = FA_FWD_POLY_PAIRS;  // of every 4 element pairs, how many use the FMA-pipe exp2
 
   // ------------------------------------------------------------------ work item
-  const int num_m_blocks = gridDim.x;
-  const int m_block = p.reverse_m ? (num_m_blocks - 1 - blockIdx.x) : blockIdx.x;
-  const int slot = blockIdx.y;                  // index over h / gp
-  const int bidb = blockIdx.z / p.num_splits;
-  const int split = blockIdx.z - bidb * p.num_splits;
+  const int num_m_blocks = p.sched_lpt ? gridDim.z : gridDim.x;
+  const int m_idx = p.sched_lpt ? blockIdx.z : blockIdx.x;
+  const int m_block = p.reverse_m ? (num_m_blocks - 1 - m_idx) : m_idx;
+  const int slot = p.sched_lpt ? blockIdx.x : blockIdx.y;   // index over h / gp
+  const int bz = p.sched_lpt ? blockIdx.y : blockIdx.z;
+  const int bidb = bz / p.num_splits;
+  const int split = bz - bidb * p.num_splits;
 
   int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
   if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
