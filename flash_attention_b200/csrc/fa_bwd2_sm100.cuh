@@ -1,9 +1,11 @@
 // fa_bwd2_sm100.cuh — backward main loop on a CTA PAIR (cluster of 2, tcgen05 cta_group::2), head dim 128.
 //
-// Why: the single-CTA kernel (fa_bwd_sm100.cuh) is bound by shared-memory bandwidth, not by the tensor pipe:
-// per 128x128 tile it moves ~480 KB through shared memory (5 SS/TS MMAs read 256 KB of operands, Q/dO arrive by
-// TMA, dS and the fp32 dQ tile are staged) = 3750 clk at 128 B/clk against 2560 clk of MMA.  A pair MMA reads
-// each CTA's half of the B operand once for both CTAs, and the pair produces ONE dQ tile per 256 keys:
+// Why a pair: the single-CTA kernel (fa_bwd_sm100.cuh) handles one tile at a time in a strictly serial chain
+// (S^T -> P^T -> dV, dP^T -> dS^T -> dK, dQ -> drain -> next dP^T): measured period 5.3k clk per 128x128 tile for 3.7k clk
+// of tcgen05.mma issue cost (experiments/mma_rate_probe.cu: TS 74 clk, SS 105 clk per 128x128x16), because its 512 TMEM
+// columns are full (S^T/P^T/dS^T 128, dP^T/dQ 128, dV 128, dK 128) and no MMA of the next tile can start early.
+// A pair produces ONE dQ tile per 256 keys, so dQ needs 64 TMEM columns per CTA instead of 128 -- that is the
+// room the schedule below needs (timeline in profiles/r01_pair_timeline_scheduleD.txt).
 //
 //   two CTAs = two adjacent 128-key blocks of one (batch, kv head), iterating the same (q head, query block) list
 //   S^T  = K Q^T       pair SS  M=256 (128 keys / CTA)  N=128 queries   B: CTA r holds query rows [64r, 64r+64)
@@ -11,10 +13,10 @@
 //   dV  += P^T dO      pair TS  M=256  N=128 (d)                        B: CTA r holds d columns [64r, 64r+64)
 //   dK  += dS^T Q      pair TS  same shape
 //   dQ   = dS K        pair SS  M=128 (64 queries / CTA)  N=128 (d)  K-dim = 256 keys of the pair
-//                      A: CTA r holds dS^T[256 keys, query half r] -- the half computed by the peer arrives through
-//                      distributed shared memory (st.shared::cluster);  B: CTA r holds K[256 keys, d half r]
-//   per CTA and tile: 64 KB TMA + 192 KB MMA operand reads + 32 KB dS + 64 KB dQ staging = 352 KB (was 480 KB);
-//   the dQ reduce-add traffic to L2 halves as well.
+//                      A: CTA r holds dS^T[256 keys, query half r] -- the half computed by the peer is staged and shipped
+//                      with cp.async.bulk.shared::cluster (tx-counted on the receiver's mbarrier);
+//                      B: CTA r holds K[256 keys, d half r]
+//   issue order per tile n:  dV(n), S^T(n+1), dK(n), dP^T(n+1), dQ(n)   (TMEM tenants: see the MMA issuer below)
 //
 // Same semantics, statistics, masks, dropout, GQA loop and epilogue as fa_bwd_kernel (reference:
 // csrc/flash_attn/src/flash_bwd_kernel.h:80-795); TMEM layouts of pair MMAs measured with
