@@ -24,6 +24,13 @@ inline bool sched_lpt(bool masked) {
   static int mode = [] { const char* e = getenv("FA_B200_SCHED"); return e ? atoi(e) : 0; }();
   return mode == 1 || (mode == 2 && masked);
 }
+// backward: chunk size (in key-block pairs / key blocks) of the chunked work-major order, 0 = head-major.
+// FA_B200_SCHED_CHUNK=c forces c for masked problems (negative: for all problems).
+inline int sched_chunk(bool masked) {
+  static int c = [] { const char* e = getenv("FA_B200_SCHED_CHUNK"); return e ? atoi(e) : 0; }();
+  if (c < 0) return -c;
+  return masked ? c : 0;
+}
 }  // namespace fa
 
 #include "fa_dropout.cuh"

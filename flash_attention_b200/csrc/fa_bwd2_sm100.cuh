@@ -73,8 +73,9 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   using Cfg = Bwd2Cfg;
   constexpr int kD = 128;
   const uint32_t rank = cluster_ctarank();
-  // grid (2 * pairs, h_k, b), or with sched_lpt (2, h_k * b, pairs): pair index slowest = heavy (masked) pairs first
-  const int pair = p.sched_lpt ? blockIdx.z : blockIdx.x >> 1;
+  // grid (2 * pairs, h_k, b): head-major; or with sched_lpt = c > 0 (2c, h_k * b, ceil(pairs / c)): chunks of c adjacent
+  // pairs of one head stay together (they share Q/dO through L2), chunk index slowest = heavy (causal) chunks of all heads first
+  const int pair = p.sched_lpt ? int(blockIdx.z) * p.sched_lpt + int(blockIdx.x >> 1) : int(blockIdx.x >> 1);
   const int hk = p.sched_lpt ? blockIdx.y % p.h_k : blockIdx.y, bidb = p.sched_lpt ? blockIdx.y / p.h_k : blockIdx.z;
   int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
   if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }

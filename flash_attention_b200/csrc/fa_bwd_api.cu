@@ -81,7 +81,10 @@ static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t st
     configured = true;
   }
   grid.x = (grid.x + 1) / 2 * 2;  // whole pairs (compile-time cluster dims (2,1,1))
-  if (kp.sched_lpt) grid = dim3(2, grid.y * grid.z, grid.x / 2);
+  if (kp.sched_lpt) {
+    const unsigned pairs = grid.x / 2, c = unsigned(kp.sched_lpt);
+    grid = dim3(2 * c, grid.y * grid.z, (pairs + c - 1) / c);
+  }
   kern<<<grid, Bwd2Cfg::kThreads, Bwd2Cfg::kSmemBytes, stream>>>(kp);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
@@ -171,7 +174,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   else { kp.softcap_pre = 0.f; kp.scale_eff = a.softmax_scale; }
   kp.scale_log2 = kp.scale_eff * float(M_LOG2E);
   dim3 grid((a.seqlen_k + 127) / 128, a.h_k, a.b);
-  kp.sched_lpt = sched_lpt(pl.has_left || pl.has_right) && grid.x <= 65535 && int64_t(a.h_k) * a.b <= 65535 ? 1 : 0;
+  kp.sched_lpt = int64_t(a.h_k) * a.b <= 65535 ? sched_chunk(pl.has_left || pl.has_right) : 0;
   int rc = 0;
   bool launched = false;
   if (a.p_dropout > 0.f) {
