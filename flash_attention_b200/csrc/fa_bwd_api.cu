@@ -105,14 +105,23 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   float* dpsum = reinterpret_cast<float*>(ws + pl.off_dps);
   float* dq_accum = reinterpret_cast<float*>(ws + pl.off_dq);
   const int sq_r = pl.sq_r;
-  cudaError_t e = cudaMemsetAsync(dq_accum, 0, pl.total - pl.off_dq, stream);  // dq_accum + semaphores
-  if (e != cudaSuccess) return set_error(std::string("cudaMemsetAsync(dq_accum): ") + cudaGetErrorString(e));
+  // dq_accum is cleared by the preprocess kernel (same pass that reads O / dO); only the deterministic-mode
+  // semaphores (and the fp16-accumulator experiment build) still need a memset
+  cudaError_t e = cudaSuccess;
+  float* clear_rows = dq_accum;
+  if (FA_BWD_DQ_FP16) {
+    clear_rows = nullptr;
+    e = cudaMemsetAsync(dq_accum, 0, pl.total - pl.off_dq, stream);
+  } else if (a.deterministic) {
+    e = cudaMemsetAsync(ws + pl.off_sem, 0, pl.total - pl.off_sem, stream);
+  }
+  if (e != cudaSuccess) return set_error(std::string("cudaMemsetAsync(backward workspace): ") + cudaGetErrorString(e));
   {
-    dim3 grid((sq_r + 7) / 8, a.h, a.b);
+    dim3 grid((sq_r + 31) / 32, a.h, a.b);
     fa_bwd_preprocess<T><<<grid, 256, 0, stream>>>(
         reinterpret_cast<const T*>(a.out), reinterpret_cast<const T*>(a.dout), a.softmax_lse, dpsum, lse_log2, a.softmax_d,
         a.o_batch_stride, a.o_row_stride, a.o_head_stride, a.do_batch_stride, a.do_row_stride, a.do_head_stride,
-        a.cu_seqlens_q, a.b, a.h, a.seqlen_q, sq_r, a.d, a.total_q);
+        a.cu_seqlens_q, a.b, a.h, a.seqlen_q, sq_r, a.d, a.total_q, clear_rows, kD);
     g_launch_count++;
     if ((e = cudaGetLastError()) != cudaSuccess) return set_error(std::string("fa_bwd_preprocess launch: ") + cudaGetErrorString(e));
   }

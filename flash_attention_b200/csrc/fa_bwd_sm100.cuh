@@ -84,45 +84,78 @@ struct BwdCfg {
 };
 
 // ---------------------------------------------------------------------------------------------- preprocess
-// one warp per query row: D = sum_d dO*O ; lse_log2 = lse*log2e (+inf on padding rows so that P == 0 there)
+// one warp per 4 query rows (all 8 loads of a warp in flight): D = sum_d dO*O ; lse_log2 = lse*log2e (+inf on padding
+// rows so that P == 0 there); also clears the rows of the fp32 dQ accumulator (`dq_accum_rows` = kD floats per row, or
+// nullptr when the host clears it), which saves the separate 256 MB memset pass at the benchmark shape
 template <typename T>
 __global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o, const T* __restrict__ dout,
                                                          const float* __restrict__ lse, float* __restrict__ dpsum,
                                                          float* __restrict__ lse_log2, float* __restrict__ softmax_d,
                                                          int64_t o_bs, int64_t o_rs, int64_t o_hs, int64_t do_bs,
                                                          int64_t do_rs, int64_t do_hs, const int* __restrict__ cu_q,
-                                                         int b, int h, int sq, int sq_r, int d, int total_q) {
+                                                         int b, int h, int sq, int sq_r, int d, int total_q,
+                                                         float* __restrict__ dq_accum_rows, int kD) {
+  constexpr int kRows = 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;  // in [0, sq_r)
+  const int row0 = (blockIdx.x * 8 + warp) * kRows;  // in [0, sq_r)
   const int head = blockIdx.y, bidb = blockIdx.z;
-  if (row >= sq_r) return;
+  if (row0 >= sq_r) return;
   int q_off = 0, sq_b = sq;
   if (cu_q) { q_off = cu_q[bidb]; sq_b = cu_q[bidb + 1] - q_off; }
-  const int64_t sidx = (int64_t(bidb) * h + head) * sq_r + row;
-  float acc = 0.f, l2 = INFINITY;
-  if (row < sq_b) {
-    const T* po = o + (cu_q ? 0 : bidb * o_bs) + int64_t(q_off + row) * o_rs + int64_t(head) * o_hs;
-    const T* pd = dout + (cu_q ? 0 : bidb * do_bs) + int64_t(q_off + row) * do_rs + int64_t(head) * do_hs;
-    for (int c = lane * 4; c < d; c += 128) {
-      const uint2 a = *reinterpret_cast<const uint2*>(po + c);
-      const uint2 g = *reinterpret_cast<const uint2*>(pd + c);
-      const T* av = reinterpret_cast<const T*>(&a);
-      const T* gv = reinterpret_cast<const T*>(&g);
+  const int64_t sidx0 = (int64_t(bidb) * h + head) * sq_r + row0;
+  const T* po = o + (cu_q ? 0 : bidb * o_bs) + int64_t(head) * o_hs;
+  const T* pd = dout + (cu_q ? 0 : bidb * do_bs) + int64_t(head) * do_hs;
+  float acc[kRows], l2[kRows];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc += float(av[e]) * float(gv[e]);
+  for (int r = 0; r < kRows; ++r) { acc[r] = 0.f; l2[r] = INFINITY; }
+  for (int c = lane * 4; c < d; c += 128) {
+    uint2 a[kRows], g[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      a[r] = g[r] = make_uint2(0u, 0u);
+      if (row0 + r < sq_b) {
+        a[r] = *reinterpret_cast<const uint2*>(po + int64_t(q_off + row0 + r) * o_rs + c);
+        g[r] = *reinterpret_cast<const uint2*>(pd + int64_t(q_off + row0 + r) * do_rs + c);
+      }
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    const float l = cu_q ? lse[int64_t(head) * total_q + q_off + row] : lse[(int64_t(bidb) * h + head) * sq + row];
-    l2 = l * 1.4426950408889634f;  // +inf stays +inf (fully masked row), -inf cannot occur for non-split forward
+    for (int r = 0; r < kRows; ++r) {
+      const T* av = reinterpret_cast<const T*>(&a[r]);
+      const T* gv = reinterpret_cast<const T*>(&g[r]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[r] += float(av[e]) * float(gv[e]);
+    }
   }
-  if (lane == 0) {
-    dpsum[sidx] = acc;
-    lse_log2[sidx] = l2;
-    // API-visible softmax_d in the reference layouts: dense (b,h,sq_r) | varlen (h, total_q + 128*b)
-    if (softmax_d) {
-      if (cu_q) { if (row < sq_b || row < ((sq_b + 127) / 128) * 128) softmax_d[int64_t(head) * (total_q + 128 * b) + q_off + 128 * bidb + row] = acc; }
-      else softmax_d[sidx] = acc;
+  if (dq_accum_rows) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      if (row0 + r < sq_r && lane * 4 < kD)
+        *reinterpret_cast<float4*>(dq_accum_rows + (sidx0 + r) * kD + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], s);
+  }
+  if (lane < kRows) {
+    const int row = row0 + lane;
+    float my_acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) my_acc = lane == r ? acc[r] : my_acc;
+    if (row < sq_r) {
+      float my_l2 = INFINITY;
+      if (row < sq_b) {
+        const float l = cu_q ? lse[int64_t(head) * total_q + q_off + row] : lse[(int64_t(bidb) * h + head) * sq + row];
+        my_l2 = l * 1.4426950408889634f;  // +inf stays +inf (fully masked row), -inf cannot occur for non-split forward
+      }
+      const int64_t sidx = sidx0 + lane;
+      dpsum[sidx] = my_acc;
+      lse_log2[sidx] = my_l2;
+      // API-visible softmax_d in the reference layouts: dense (b,h,sq_r) | varlen (h, total_q + 128*b)
+      if (softmax_d) {
+        if (cu_q) { if (row < ((sq_b + 127) / 128) * 128) softmax_d[int64_t(head) * (total_q + 128 * b) + q_off + 128 * bidb + row] = my_acc; }
+        else softmax_d[sidx] = my_acc;
+      }
     }
   }
 }
