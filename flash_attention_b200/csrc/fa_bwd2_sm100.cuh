@@ -43,8 +43,14 @@ __device__ unsigned long long g_bwd2_ts[2 * 16 * 32];   // [rank][iteration - 8]
     if (pair == 0 && hk == 0 && bidb == 0 && it >= 8 && it < 24)                      \
       g_bwd2_ts[(int(rank) * 16 + (it - 8)) * 32 + (ev)] = clock64();                                    \
   } while (0)
+// once-per-CTA stamps (prologue / epilogue): slot [rank][15][ev]
+#define TSX(ev)                                                                                         \
+  do {                                                                                                  \
+    if (pair == 0 && hk == 0 && bidb == 0) g_bwd2_ts[(int(rank) * 16 + 15) * 32 + (ev)] = clock64();      \
+  } while (0)
 #else
 #define TS(ev) do {} while (0)
+#define TSX(ev) do {} while (0)
 #endif
 
 struct Bwd2Cfg {
@@ -120,6 +126,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSBar + 8 * Cfg::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TSX(0);
   if (warp == 13 && lane == 0) {
     tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_do); tma_prefetch_desc(&p.tm_k); tma_prefetch_desc(&p.tm_v);
     tma_prefetch_desc(&p.tm_q64); tma_prefetch_desc(&p.tm_do64); tma_prefetch_desc(&p.tm_dq64);
@@ -146,9 +153,11 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     tmem_alloc_pair(sTmemPtr, 512);
     tmem_relinquish_pair();
   }
+  if (threadIdx.x == 0) TSX(1);
   tc_fence_before();
   cluster_sync_all();   // barriers of both CTAs initialised, both TMEM allocations done
   tc_fence_after();
+  if (threadIdx.x == 0) TSX(2);
   const uint32_t tmem_base = *tmem_ptr_gen;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 384;
 
@@ -242,7 +251,9 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         };
         const uint32_t lo_ds = lo_mn(sDS), lo_kt = lo_mn(sKt);
         mbar_wait(bar(F_KV), 0, 500);
+        TSX(3);
         mbar_wait(bar(F_QB), 0, 501);
+        TSX(4);
         tc_fence_after();
         mma_kmajor(tS, sK, sQb);
         mma_commit_pair(bar(S_F));
@@ -323,6 +334,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
 #endif
         }
         mma_commit_pair(bar(DKV_F));
+        TSX(5);
       }
       if (rank == 1 && elect_one()) {
         // relay: tell the leader when this CTA's dS^T tile (local stores + the peer's st.async) is complete
@@ -595,9 +607,46 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     // ---------------------------------------------------------------- epilogue: dK (x scale), dV (x 1/p_keep)
     if (n_iter > 0) {
       mbar_wait(bar(DKV_F), 0, 710);
+      if (threadIdx.x == 0) TSX(6);
       tc_fence_after();
     }
     const int bk = p.cu_seqlens_k ? 0 : bidb;
+    // Fast path: the 128 x 128 dV / dK tiles go through the (now idle) V / K shared-memory tiles and leave with TMA
+    // stores (rows / columns beyond the tensor are clipped by the tensor map).  A ragged tail block of a PACKED varlen
+    // batch borders the next sequence's rows, so it takes the predicated per-thread path, as does an empty work item.
+    const bool tma_epilogue = n_iter > 0 && !(p.cu_seqlens_k && key0 + 128 > sk_b);
+    if (tma_epilogue) {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t t_src = (which == 0 ? tDV : tDK) + lane_sel + hf * 64;
+        const float mul = which == 0 ? (kDropout ? drop.rp : 1.0f) : p.scale;
+        uint8_t* dst = smem_gen + (which == 0 ? Cfg::kSV : Cfg::kSK) + hf * 16384 + r * 128;   // panel hf = d columns [64 hf, 64 hf + 64)
+        uint32_t o[64];
+        tmem_ld_x32(t_src, o);
+        tmem_ld_x32(t_src + 32, o + 32);
+        tmem_wait_ld();
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          uint4 v4;
+          v4.x = Elt<T>::pack(__uint_as_float(o[8 * x + 0]) * mul, __uint_as_float(o[8 * x + 1]) * mul);
+          v4.y = Elt<T>::pack(__uint_as_float(o[8 * x + 2]) * mul, __uint_as_float(o[8 * x + 3]) * mul);
+          v4.z = Elt<T>::pack(__uint_as_float(o[8 * x + 4]) * mul, __uint_as_float(o[8 * x + 5]) * mul);
+          v4.w = Elt<T>::pack(__uint_as_float(o[8 * x + 6]) * mul, __uint_as_float(o[8 * x + 7]) * mul);
+          *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) = v4;
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(7, 256);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int pn = 0; pn < 2; ++pn) {
+          tma_store_4d(&p.tm_dv, sV + pn * 16384, pn * 64, k_off + key0, hk, bk);
+          tma_store_4d(&p.tm_dk, sK + pn * 16384, pn * 64, k_off + key0, hk, bk);
+        }
+        tma_store_commit();
+        tma_store_wait_read<0>();   // shared memory must outlive the reads; the writes complete on their own
+      }
+    } else {
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const uint32_t t_src = (which == 0 ? tDV : tDK) + lane_sel;
@@ -632,10 +681,13 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         }
       }
     }
+    }
   }
 
+  if (threadIdx.x == 0) TSX(7);
   tc_fence_before();
   cluster_sync_all();   // nobody leaves while the peer may still signal its barriers or write its shared memory
+  if (threadIdx.x == 0) TSX(8);
   if (warp == 12) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);

@@ -160,6 +160,8 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
       uint32_t box[4] = {64, 64, 1, 1};
       return make_tmap(tm, dt, 4, base, dims, str, box);
     };
+    if (int rc = map16(&kp.tm_dk, a.dk, a.dk_batch_stride, a.dk_row_stride, a.dk_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
+    if (int rc = map16(&kp.tm_dv, a.dv, a.dv_batch_stride, a.dv_row_stride, a.dv_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
     if (int rc = map64(&kp.tm_q64, a.q, a.q_batch_stride, a.q_row_stride, a.q_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
     if (int rc = map64(&kp.tm_do64, a.dout, a.do_batch_stride, a.do_row_stride, a.do_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
     uint64_t dims[4] = {uint64_t(kD), uint64_t(sq_r), uint64_t(a.h), uint64_t(a.b)};

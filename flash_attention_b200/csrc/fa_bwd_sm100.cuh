@@ -35,6 +35,7 @@ struct BwdKernelParams {
   CUtensorMap tm_dq;         // 4-D (kD, sq_r, h, b) fp32, box (32, 128, 1, 1), 128B swizzle, reduce-add target
   CUtensorMap tm_q64, tm_do64;  // CTA-pair kernel (fa_bwd2_sm100.cuh): the same tensors with box (64, 64, 1, 1)
   CUtensorMap tm_dq64;          // CTA-pair kernel: dq_accum with box (32, 64, 1, 1)
+  CUtensorMap tm_dk, tm_dv;     // CTA-pair kernel epilogue: dK / dV outputs, box (64, 128, 1, 1)
   const float* lse_log2;     // (b, h, sq_r)
   int* dq_semaphore;         // deterministic mode: (b, h, sq_r/128) counters, zero-initialised; else nullptr
   const float* dpsum;        // (b, h, sq_r)

@@ -39,3 +39,8 @@ for rank in range(2):
                 row.append(f"{nm}={t - base:+d}")
         prev = int(ts[rank, it - 1, 0]) if rank == 0 else int(ts[rank, it - 1, 8])
         print(f"it {it + 8}: period {base - prev} | " + " ".join(row))
+
+x = ts[0, 15]
+names_x = ["entry", "before cluster sync", "after cluster sync", "K/V landed", "Q landed", "last MMA issued", "all MMA done (compute sees)",
+           "epilogue stores issued", "after final cluster sync"]
+print("once-per-CTA stamps (leader, clk since entry):", ", ".join(f"{n}={int(x[i]) - int(x[0])}" for i, n in enumerate(names_x) if int(x[i])))
