@@ -511,6 +511,12 @@ int fa_b200_kvcache_append(const fa_b200_append_args* a, fa_b200_stream_t stream
 }
 size_t fa_b200_sizeof_append_args(void) { return sizeof(fa_b200_append_args); }
 
+#if FA_FWD_TS
+// timeline-debugging builds only (not declared in include/fa_b200.h)
+int fa_b200_debug_read_fwd_ts(unsigned long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, fa::g_fwd_ts, size_t(n) * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
 const char* fa_b200_last_error(void) { return g_last_error.c_str(); }
 size_t fa_b200_sizeof_fwd_args(void) { return sizeof(fa_b200_fwd_args); }
 size_t fa_b200_sizeof_bwd_args(void) { return sizeof(fa_b200_bwd_args); }

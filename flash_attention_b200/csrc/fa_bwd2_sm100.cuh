@@ -413,7 +413,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sem), "r"(my_turn + 1) : "memory");
       }
     }
-    if (leader) tma_store_wait<0>();
+    if (leader) tma_store_wait_read<0>();   // the staging buffers must outlive the reads; completion is the grid's business
   } else {
     // ================================================================ compute warps (as in fa_bwd_kernel)
     reg_alloc<Cfg::kRegsCompute>();
