@@ -108,6 +108,7 @@ SYMBOLS = {
     "fa_b200_fwd_combine": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp]),
     "fa_b200_kvcache_append": (C.c_int, [C.POINTER(AppendArgs), _vp]),
     "fa_b200_sizeof_append_args": (_sz, []),
+    "fa_b200_memcpy2d_async": (C.c_int, [_vp, _sz, _vp, _sz, _sz, _sz, _i32, _vp]),
     "fa_b200_num_splits_heuristic": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fa_b200_last_error": (C.c_char_p, []),
     "fa_b200_sizeof_fwd_args": (_sz, []),

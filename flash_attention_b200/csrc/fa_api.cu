@@ -517,6 +517,14 @@ int fa_b200_debug_read_fwd_ts(unsigned long long* out, int n) {
   return cudaMemcpyFromSymbol(out, fa::g_fwd_ts, size_t(n) * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
 }
 #endif
+int fa_b200_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t height,
+                           int32_t kind, fa_b200_stream_t stream) {
+  if (kind != 1 && kind != 2) return set_error("fa_b200_memcpy2d_async: kind must be 1 (host->device) or 2 (device->host)");
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height,
+                                    kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_error(std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(e));
+  return 0;
+}
 const char* fa_b200_last_error(void) { return g_last_error.c_str(); }
 size_t fa_b200_sizeof_fwd_args(void) { return sizeof(fa_b200_fwd_args); }
 size_t fa_b200_sizeof_bwd_args(void) { return sizeof(fa_b200_bwd_args); }

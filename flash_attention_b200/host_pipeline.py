@@ -1,17 +1,22 @@
 """Host-buffer entry point: attention forward (+ backward) on tensors that live in pinned HOST memory.
 
 The C ABI works on device pointers; a caller that owns host buffers (the reference-facing plugin call measured
-as `e2e` by bench.py) would otherwise pay H2D -> compute -> D2H back to back.  This helper splits the batch into
-chunks and runs a 3-stage pipeline on three CUDA streams (H2D of chunk i+1 | kernels of chunk i | D2H of chunk
-i-1), so the step costs ~max(H2D, compute, D2H) instead of their sum.  Attention is independent per batch
-element, so chunking does not change any result bit.
+as `e2e` by bench.py) would otherwise pay H2D -> compute -> D2H back to back.  This helper cuts the problem into
+(batch chunk x kv-head group) pieces -- attention is independent per batch element and per kv head, so no result bit
+changes -- and runs a 3-stage pipeline on three CUDA streams (H2D of piece i+1 | kernels of piece i | D2H of
+piece i-1).  A head group of a `(b, s, h, d)` host tensor is a pitched 2-D region, moved with one
+`fa_b200_memcpy2d_async` (cudaMemcpy2DAsync) per tensor into / out of dense device staging buffers.  The step then
+costs ~max(H2D, D2H) + one small piece of fill / drain; with 16 pieces at the benchmark shape the PCIe link is busy
+in both directions for most of the step.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
 
 import torch
 
+from . import _lib
 from . import flash_attn_2_cuda as _op
 
 
@@ -19,26 +24,56 @@ class HostAttentionPipeline:
     """Re-usable pipeline (streams, device staging buffers) for one problem shape."""
 
     def __init__(self, batch, seqlen_q, seqlen_k, nheads, nheads_k, headdim, dtype=torch.bfloat16, device="cuda",
-                 chunks: Optional[int] = None, backward=True):
+                 chunks: Optional[int] = None, backward=True, head_groups: Optional[int] = None):
         self.dev = torch.device(device)
         self.b, self.bwd = batch, backward
         self.chunks = chunks or batch
         assert batch % self.chunks == 0
         cb = batch // self.chunks
         self.cb = cb
+        # kv-head groups per batch chunk: aim at ~16 pieces in total
+        if head_groups is None:
+            head_groups = 1
+            while self.chunks * head_groups < 16 and nheads_k % (head_groups * 2) == 0:
+                head_groups *= 2
+        assert nheads_k % head_groups == 0
+        self.hg = head_groups
+        self.hkc = nheads_k // head_groups          # kv heads per piece
+        self.hqc = nheads // head_groups            # query heads per piece (whole GQA groups)
+        self.h, self.hk, self.d = nheads, nheads_k, headdim
+        self.sq, self.sk = seqlen_q, seqlen_k
+        self.esz = torch.empty((), dtype=dtype).element_size()
         mk = lambda s, h: [torch.empty(cb, s, h, headdim, dtype=dtype, device=self.dev) for _ in range(2)]
-        # double-buffered device staging (chunk i+1 is uploaded while chunk i computes)
-        self.q, self.k, self.v = mk(seqlen_q, nheads), mk(seqlen_k, nheads_k), mk(seqlen_k, nheads_k)
-        self.do = mk(seqlen_q, nheads) if backward else None
-        self.out = mk(seqlen_q, nheads)
+        # double-buffered device staging (piece i+1 is uploaded while piece i computes)
+        self.q, self.k, self.v = mk(seqlen_q, self.hqc), mk(seqlen_k, self.hkc), mk(seqlen_k, self.hkc)
+        self.do = mk(seqlen_q, self.hqc) if backward else None
+        self.out = mk(seqlen_q, self.hqc)
         if backward:
-            self.dq, self.dk, self.dv = mk(seqlen_q, nheads), mk(seqlen_k, nheads_k), mk(seqlen_k, nheads_k)
+            self.dq, self.dk, self.dv = mk(seqlen_q, self.hqc), mk(seqlen_k, self.hkc), mk(seqlen_k, self.hkc)
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.scale = headdim ** -0.5
+        self.lib = _lib.load()
+
+    def _copy(self, dev_t, host_t, b0, h0, to_device, stream):
+        """dev_t (cb, s, hc, d) dense <-> host_t[b0:b0+cb, :, h0:h0+hc, :] of a dense (b, s, h, d) pinned host tensor."""
+        assert host_t.is_contiguous() and dev_t.is_contiguous()
+        cb, s, hc, d = dev_t.shape
+        h = host_t.shape[2]
+        width = hc * d * self.esz
+        hpitch = h * d * self.esz
+        hptr = host_t.data_ptr() + ((b0 * s) * h + h0) * d * self.esz
+        if to_device:
+            rc = self.lib.fa_b200_memcpy2d_async(C.c_void_p(dev_t.data_ptr()), width, C.c_void_p(hptr), hpitch, width, cb * s, 1,
+                                                 C.c_void_p(stream.cuda_stream))
+        else:
+            rc = self.lib.fa_b200_memcpy2d_async(C.c_void_p(hptr), hpitch, C.c_void_p(dev_t.data_ptr()), width, width, cb * s, 2,
+                                                 C.c_void_p(stream.cuda_stream))
+        _lib.check(rc)
 
     def run(self, hq, hk, hv, hdo, ho, hdq=None, hdk=None, hdv=None, causal=False):
-        """All h* are pinned host tensors of the full batch; results are written into ho (and hdq/hdk/hdv)."""
-        cb, n = self.cb, self.chunks
+        """All h* are pinned host tensors of the full problem; results are written into ho (and hdq/hdk/hdv)."""
+        cb = self.cb
+        n = self.chunks * self.hg
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
@@ -46,15 +81,17 @@ class HostAttentionPipeline:
         ev_cmp = [torch.cuda.Event() for _ in range(n)]
         ev_out = [torch.cuda.Event() for _ in range(n)]
         for i in range(n):
-            sl, bsel = slice(i * cb, (i + 1) * cb), i & 1
+            b0, g = (i // self.hg) * cb, i % self.hg
+            hq0, hk0 = g * self.hqc, g * self.hkc
+            bsel = i & 1
             with torch.cuda.stream(self.s_in):
                 if i >= 2:
-                    self.s_in.wait_event(ev_cmp[i - 2])  # staging buffer bsel is free once chunk i-2 has computed
-                self.q[bsel].copy_(hq[sl], non_blocking=True)
-                self.k[bsel].copy_(hk[sl], non_blocking=True)
-                self.v[bsel].copy_(hv[sl], non_blocking=True)
+                    self.s_in.wait_event(ev_cmp[i - 2])  # staging buffer bsel is free once piece i-2 has computed
+                self._copy(self.q[bsel], hq, b0, hq0, True, self.s_in)
+                self._copy(self.k[bsel], hk, b0, hk0, True, self.s_in)
+                self._copy(self.v[bsel], hv, b0, hk0, True, self.s_in)
                 if self.bwd:
-                    self.do[bsel].copy_(hdo[sl], non_blocking=True)
+                    self._copy(self.do[bsel], hdo, b0, hq0, True, self.s_in)
                 ev_in[i].record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(ev_in[i])
@@ -68,11 +105,11 @@ class HostAttentionPipeline:
                 ev_cmp[i].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_cmp[i])
-                ho[sl].copy_(self.out[bsel], non_blocking=True)
+                self._copy(self.out[bsel], ho, b0, hq0, False, self.s_out)
                 if self.bwd:
-                    hdq[sl].copy_(self.dq[bsel], non_blocking=True)
-                    hdk[sl].copy_(self.dk[bsel], non_blocking=True)
-                    hdv[sl].copy_(self.dv[bsel], non_blocking=True)
+                    self._copy(self.dq[bsel], hdq, b0, hq0, False, self.s_out)
+                    self._copy(self.dk[bsel], hdk, b0, hk0, False, self.s_out)
+                    self._copy(self.dv[bsel], hdv, b0, hk0, False, self.s_out)
                 ev_out[i].record(self.s_out)
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_cmp)

@@ -170,6 +170,12 @@ typedef struct fa_b200_append_args {
 int fa_b200_kvcache_append(const fa_b200_append_args* args, fa_b200_stream_t stream);
 size_t fa_b200_sizeof_append_args(void);
 
+/* ---- host-buffer plumbing: pitched copy between a (pinned) host tensor slice and a dense device buffer, used by the
+ *      host-buffer pipeline to move one (batch chunk, head group) at a time.  kind: 1 = host -> device, 2 = device -> host.
+ *      `height` rows of `width_bytes`; pitches in bytes.  Asynchronous on `stream`. */
+int fa_b200_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                           size_t height, int32_t kind, fa_b200_stream_t stream);
+
 /* ---- helpers ---- */
 int fa_b200_num_splits_heuristic(int batch_nheads_mblocks, int num_sms, int num_n_blocks, int max_splits);
 const char* fa_b200_last_error(void);

@@ -1,12 +1,13 @@
 """Host-buffer entry point (the call bench.py's e2e leg times): results must be bit-identical to the device API,
-because chunking over the batch does not change any per-(batch, head) computation."""
+because cutting the problem into (batch chunk x kv-head group) pieces does not change any per-(batch, head) computation."""
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
 
-def test_host_pipeline_matches_device_api():
+@pytest.mark.parametrize("head_groups", [None, 1, 2])
+def test_host_pipeline_matches_device_api(head_groups):
     import flash_attention_b200 as fab
     from flash_attention_b200.host_pipeline import HostAttentionPipeline
 
@@ -15,7 +16,7 @@ def test_host_pipeline_matches_device_api():
     hq, hk_, hv, hdo = pin(b, s, h, d), pin(b, s, hk, d), pin(b, s, hk, d), pin(b, s, h, d)
     ho, hdq = torch.empty_like(hq).pin_memory(), torch.empty_like(hq).pin_memory()
     hdk, hdv = torch.empty_like(hk_).pin_memory(), torch.empty_like(hv).pin_memory()
-    pipe = HostAttentionPipeline(b, s, s, h, hk, d, torch.bfloat16, "cuda", chunks=b, backward=True)
+    pipe = HostAttentionPipeline(b, s, s, h, hk, d, torch.bfloat16, "cuda", chunks=b, backward=True, head_groups=head_groups)
     for _ in range(2):  # second run re-uses the staging buffers
         pipe.run(hq, hk_, hv, hdo, ho, hdq, hdk, hdv, causal=True)
     torch.cuda.synchronize()
