@@ -17,15 +17,16 @@ int set_error(const std::string& msg);
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 int num_sms();
-// Work-major (longest-first) block order, opt-in with FA_B200_SCHED=1 (=2: masked problems only).  Measured slower
-// than the head-major default on B200 (causal bwd 1024 -> 916, causal fwd 1083 -> 1028, non-causal bwd 1179 -> 948
-// TFLOP/s): CTAs of one head that run together share Q/dO (bwd) or K/V (fwd) through L2, which matters more than the tail.
-inline bool sched_lpt(bool masked) {
-  static int mode = [] { const char* e = getenv("FA_B200_SCHED"); return e ? atoi(e) : 0; }();
-  return mode == 1 || (mode == 2 && masked);
+// Block order.  Default is head-major (all blocks of one head are dispatched together: they share their streamed operands
+// through L2, which measured more important than a balanced tail: pure work-major order cost 10 % on causal problems).
+// The chunked work-major order keeps chunks of c adjacent blocks of a head together and dispatches heavy chunks of all
+// heads first; it buys 0.5-1.7 % on the causal forward (default c = 16 there) and nothing on the backward (default off).
+// forward: FA_B200_SCHED_CHUNK_FWD=c (m-blocks per chunk) for masked problems, negative: for all problems; 0 = head-major
+inline int sched_chunk_fwd(bool masked) {
+  static int c = [] { const char* e = getenv("FA_B200_SCHED_CHUNK_FWD"); return e ? atoi(e) : 16; }();
+  if (c < 0) return -c;
+  return masked ? c : 0;
 }
-// backward: chunk size (in key-block pairs / key blocks) of the chunked work-major order, 0 = head-major.
-// FA_B200_SCHED_CHUNK=c forces c for masked problems (negative: for all problems).
 inline int sched_chunk(bool masked) {
   static int c = [] { const char* e = getenv("FA_B200_SCHED_CHUNK"); return e ? atoi(e) : 0; }();
   if (c < 0) return -c;

@@ -59,8 +59,8 @@ struct FwdKernelParams {
   int has_right, has_left;  // window limits active (causal => has_right, wr = 0)
   int wl, wr;
   int reverse_m;            // schedule heavy m-blocks first (causal)
-  int sched_lpt;            // grid = (head slots, batch x splits, m blocks): the m-block index is the SLOWEST grid dimension,
-                            // so with a mask all heads' heaviest m-blocks are dispatched first (longest-processing-time-first)
+  int sched_lpt;            // 0: head-major grid; c > 0: chunked work-major grid (see the work-item prologue)
+  int num_m_blocks;
   float scale;              // effective softmax scale (softcap if softcap > 0)
   float scale_log2;         // scale * log2(e)
   float softcap_pre;        // softmax_scale / softcap, 0 = off
@@ -150,11 +150,16 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   constexpr int kPolyPairs = FA_FWD_POLY_PAIRS;  // of every 4 element pairs, how many use the FMA-pipe exp2
 
   // ------------------------------------------------------------------ work item
-  const int num_m_blocks = p.sched_lpt ? gridDim.z : gridDim.x;
-  const int m_idx = p.sched_lpt ? blockIdx.z : blockIdx.x;
+  // default grid (m blocks, head slots, batch x splits).  sched_lpt = c > 0: grid (c, head slots x batch x splits,
+  // ceil(m blocks / c)) -- chunks of c adjacent m-blocks of one head stay together (they share K/V through L2) and the
+  // chunk index is the slowest dimension, so with a causal mask every head's heavy chunks are dispatched first
+  const int num_m_blocks = p.num_m_blocks;
+  const int m_idx = p.sched_lpt ? int(blockIdx.z) * p.sched_lpt + int(blockIdx.x) : int(blockIdx.x);
+  if (m_idx >= num_m_blocks) return;
   const int m_block = p.reverse_m ? (num_m_blocks - 1 - m_idx) : m_idx;
-  const int slot = p.sched_lpt ? blockIdx.x : blockIdx.y;   // index over h / gp
-  const int bz = p.sched_lpt ? blockIdx.y : blockIdx.z;
+  const int nslots = p.h / p.gp;
+  const int slot = p.sched_lpt ? int(blockIdx.y) % nslots : int(blockIdx.y);   // index over h / gp
+  const int bz = p.sched_lpt ? int(blockIdx.y) / nslots : int(blockIdx.z);
   const int bidb = bz / p.num_splits;
   const int split = bz - bidb * p.num_splits;
 
