@@ -341,7 +341,8 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   dim3 grid(pl.num_m_blocks, a.h / gp, a.b * pl.num_splits);
   // masked work is uneven across m-blocks: dispatch every head's heavy m-blocks first (m-block = slowest grid dimension)
   kp.num_m_blocks = pl.num_m_blocks;
-  if (const int c = sched_chunk_fwd(pl.has_left || pl.has_right); c > 0 && int64_t(grid.y) * grid.z <= 65535) {
+  if (const int c = sched_chunk_fwd(pl.has_left || pl.has_right);
+      c > 0 && pl.num_m_blocks > c && int64_t(grid.y) * grid.z <= 65535) {   // short problems keep the plain grid
     kp.sched_lpt = c;
     grid = dim3(c, grid.y * grid.z, (pl.num_m_blocks + c - 1) / c);
   }
