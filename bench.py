@@ -206,7 +206,7 @@ def main():
         step()
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("FA_BENCH_NO_SAMPLER"):
         sampler.start()
     launches0 = lib.fa_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
