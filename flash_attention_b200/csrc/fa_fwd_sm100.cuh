@@ -133,6 +133,12 @@ __device__ unsigned long long g_fwd_ts[16 * 16];   // [iteration - 8][event]
 #define FTS(ev) do {} while (0)
 #endif
 
+#ifndef FA_FWD_POLY_PAIRS_FP8
+#define FA_FWD_POLY_PAIRS_FP8 1
+#endif
+#ifndef FA_FWD_POLY_DEG_FP8
+#define FA_FWD_POLY_DEG_FP8 3
+#endif
 #ifndef FA_FWD_POLY_PAIRS
 #define FA_FWD_POLY_PAIRS 1  // measured on B200 (r01): 0 -> 1315, 1 -> 1339, 2 -> 1307, 3 -> 1147, 4 -> 1046 TFLOP/s fwd
 #endif
@@ -147,7 +153,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   constexpr int kRowsPerCta = 128 * kTiles;
   constexpr int S = Cfg::kStages;
   constexpr float kNegInf = -INFINITY;
-  constexpr int kPolyPairs = FA_FWD_POLY_PAIRS;  // of every 4 element pairs, how many use the FMA-pipe exp2
+  // of every 4 element pairs, how many use the FMA-pipe exp2 (fp8 has its own setting: its P is quantised to e4m3)
+  constexpr int kPolyPairs = kFp8 ? FA_FWD_POLY_PAIRS_FP8 : FA_FWD_POLY_PAIRS;
+  constexpr int kPolyDeg = kFp8 ? FA_FWD_POLY_DEG_FP8 : 3;
 
   // ------------------------------------------------------------------ work item
   // default grid (m blocks, head slots, batch x splits).  sched_lpt = c > 0: grid (c, head slots x batch x splits,
@@ -555,7 +563,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
               e0 = ex2(x0);
               e1 = ex2(x1);
             } else {
-              ex2_poly2(x0, x1, e0, e1);
+              if constexpr (kPolyDeg == 2) ex2_poly2_deg2(x0, x1, e0, e1);
+              else ex2_poly2(x0, x1, e0, e1);
             }
             if (c & 2) acc_b = add2(acc_b, pack2(e0, e1));
             else acc_a = add2(acc_a, pack2(e0, e1));

@@ -357,6 +357,25 @@ __device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& 
   r1 = z1 ? 0.f : __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
+// degree-2 variant (rel. err 1.7e-3): enough when the result is quantised to e4m3 (3 mantissa bits); one FFMA2 less
+__device__ __forceinline__ void ex2_poly2_deg2(float x0, float x1, float& r0, float& r1) {
+  const float kMagic = 12582912.0f;
+  const bool z0 = x0 < -125.0f, z1 = x1 < -125.0f;
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t t = add2(x, pack2(kMagic, kMagic));
+  const uint64_t n = add2(t, pack2(-kMagic, -kMagic));
+  const uint64_t f = fma2(n, pack2(-1.0f, -1.0f), x);
+  uint64_t pl = fma2(f, pack2(0.23842086f, 0.23842086f), pack2(0.70343314f, 0.70343314f));
+  pl = fma2(pl, f, pack2(1.00044256f, 1.00044256f));
+  float t0, t1, p0, p1;
+  unpack2(t, t0, t1);
+  unpack2(pl, p0, p1);
+  r0 = z0 ? 0.f : __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = z1 ? 0.f : __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // {lo, hi} -> packed 16-bit pair (lo in bits [0,16))
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
