@@ -37,6 +37,8 @@ namespace fa {
 #define FA_BWD2_TS 0     // 1: CTA pair (0,0,0) records clock64 stamps of its pipeline events (timeline debugging build)
 #endif
 #if FA_BWD2_TS
+__device__ unsigned long long g_bwd2_span[3 * 8192];    // per CTA: smid, globaltimer at entry, at exit
+__device__ unsigned int g_bwd2_span_n;
 __device__ unsigned long long g_bwd2_ts[2 * 16 * 32];   // [rank][iteration - 8][event]
 #define TS(ev)                                                                                          \
   do {                                                                                                  \
@@ -127,6 +129,18 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TSX(0);
+#if FA_BWD2_TS
+  unsigned int span_slot = 0;
+  if (threadIdx.x == 0) {
+    span_slot = atomicAdd(&g_bwd2_span_n, 1u);
+    if (span_slot < 8192) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_bwd2_span[3 * span_slot] = smid;
+      g_bwd2_span[3 * span_slot + 1] = global_timer_ns();
+    }
+  }
+#endif
   if (warp == 13 && lane == 0) {
     tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_do); tma_prefetch_desc(&p.tm_k); tma_prefetch_desc(&p.tm_v);
     tma_prefetch_desc(&p.tm_q64); tma_prefetch_desc(&p.tm_do64); tma_prefetch_desc(&p.tm_dq64);
@@ -688,6 +702,9 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   tc_fence_before();
   cluster_sync_all();   // nobody leaves while the peer may still signal its barriers or write its shared memory
   if (threadIdx.x == 0) TSX(8);
+#if FA_BWD2_TS
+  if (threadIdx.x == 0 && span_slot < 8192) g_bwd2_span[3 * span_slot + 2] = global_timer_ns();
+#endif
   if (warp == 12) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);

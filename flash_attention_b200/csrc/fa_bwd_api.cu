@@ -243,6 +243,16 @@ int fa_b200_mha_varlen_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream
 }
 #if FA_BWD2_TS
 // timeline-debugging builds only (not declared in include/fa_b200.h): copies the clock64 stamps of the pair kernel
+// per-CTA (smid, entry ns, exit ns) of the pair kernel launches since the last reset; returns the number of records
+int fa_b200_debug_read_spans(unsigned long long* out, int max_records, int reset) {
+  unsigned int n = 0;
+  cudaMemcpyFromSymbol(&n, fa::g_bwd2_span_n, sizeof n);
+  if (n > 8192u) n = 8192u;
+  if (int(n) > max_records) n = unsigned(max_records);
+  if (out) cudaMemcpyFromSymbol(out, fa::g_bwd2_span, size_t(n) * 3 * sizeof(unsigned long long));
+  if (reset) { unsigned int z = 0; cudaMemcpyToSymbol(fa::g_bwd2_span_n, &z, sizeof z); }
+  return int(n);
+}
 int fa_b200_debug_read_ts(unsigned long long* out, int n) {
   return cudaMemcpyFromSymbol(out, fa::g_bwd2_ts, size_t(n) * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
 }
