@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(256) fa_dmask_kernel(const DmaskParams p) {
       val = __expf(acc - lse);
       const uint4 r = dropout_patch(p.drop, uint32_t(i) >> 2, uint32_t(j) >> 2, uint32_t(bidb * p.h + head));
       const uint32_t byte = (select_word(r, i & 3) >> (8 * (j & 3))) & 0xffu;
-      if (byte > p.drop.thr) val = -val;
+      // dropped: negative sign.  A probability that underflows to 0 (in fp32, or when cast to fp16) would lose the sign
+      // (-0.0 >= 0 is true), so a dropped entry is stored as at most -2^-24 (smallest fp16 subnormal, exact in bf16 too)
+      if (byte > p.drop.thr) val = -fmaxf(val, 5.9604645e-8f);
     }
     out[j] = T(val);
   }
