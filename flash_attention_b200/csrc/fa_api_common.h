@@ -20,10 +20,11 @@ int num_sms();
 // Block order.  Default is head-major (all blocks of one head are dispatched together: they share their streamed operands
 // through L2, which measured more important than a balanced tail: pure work-major order cost 10 % on causal problems).
 // The chunked work-major order keeps chunks of c adjacent blocks of a head together and dispatches heavy chunks of all
-// heads first; it buys 0.5-1.7 % on the causal forward (default c = 16 there) and nothing on the backward (default off).
+// heads first; it buys 0.5-2.5 % on the causal forward but DOUBLES its DRAM reads (406 -> 813 MB at b4 h16 s8192: more heads'
+// K/V compete for L2, hit rate 90.8 -> 83.9 %), and nothing on the backward: off by default for both.
 // forward: FA_B200_SCHED_CHUNK_FWD=c (m-blocks per chunk) for masked problems, negative: for all problems; 0 = head-major
 inline int sched_chunk_fwd(bool masked) {
-  static int c = [] { const char* e = getenv("FA_B200_SCHED_CHUNK_FWD"); return e ? atoi(e) : 16; }();
+  static int c = [] { const char* e = getenv("FA_B200_SCHED_CHUNK_FWD"); return e ? atoi(e) : 0; }();
   if (c < 0) return -c;
   return masked ? c : 0;
 }
