@@ -68,6 +68,9 @@ def _workspace(lib, args, device):
     return ws
 
 
+_ZERO_RNG_STATE = {}
+
+
 def _round128(x: int) -> int:
     return (x + 127) // 128 * 128
 
@@ -76,8 +79,11 @@ def _dropout_state(a, p_dropout, gen_, device, b, h):
     """Philox (seed, offset) of this call from the CUDA generator, advanced like the reference does
     (flash_api.cpp:505-517: counter_offset = b * h * 32).  Returns the `rng_state` tensor (2,) int64."""
     _check(0.0 <= p_dropout < 1.0, "p_dropout must be in [0, 1)")
-    if p_dropout == 0.0:
-        return torch.zeros(2, dtype=torch.int64, device=device)
+    if p_dropout == 0.0:  # one shared (never written) zero state per device instead of a fill kernel per call
+        z = _ZERO_RNG_STATE.get(device)
+        if z is None:
+            z = _ZERO_RNG_STATE[device] = torch.zeros(2, dtype=torch.int64, device=device)
+        return z
     gen = gen_ if gen_ is not None else torch.cuda.default_generators[device.index if device.index is not None
                                                                        else torch.cuda.current_device()]
     seed, offset = int(gen.initial_seed()), int(gen.get_offset())
