@@ -96,3 +96,35 @@ def test_forward_plan_host_logic(fa_lib):
     # few CTAs and a long KV: split heuristic kicks in (flash_api.cpp:281-315 rule on 2 x 148 CTA slots)
     splits, gp, mblocks = op.plan_kvcache(1, 1, 16384, 8, 8, 128, 0, False, -1, -1)
     assert splits > 1
+
+
+def test_dropout_and_backward_argument_checks_without_gpu(fa_lib):
+    """Host-side validation added with dropout / the pair backward: all of it runs before any CUDA call."""
+    a = _lib.FwdArgs()
+    a.dtype = _lib.BF16
+    a.q = a.k = a.v = a.out = a.softmax_lse = 16
+    a.b, a.seqlen_q, a.seqlen_k, a.h, a.h_k, a.d = 1, 128, 128, 4, 4, 128
+    a.softmax_scale = 0.1
+    a.p_dropout = 1.0
+    assert fa_lib.fa_b200_mha_fwd(C.byref(a), None) != 0 and b"p_dropout" in fa_lib.fa_b200_last_error()
+    a.p_dropout, a.softcap = 0.1, 30.0
+    assert fa_lib.fa_b200_mha_fwd(C.byref(a), None) != 0
+    assert b"Softcapping does not support dropout" in fa_lib.fa_b200_last_error()   # flash_api.cpp:391
+    a.softcap, a.num_splits = 0.0, 4
+    assert fa_lib.fa_b200_mha_fwd(C.byref(a), None) != 0 and b"num_splits" in fa_lib.fa_b200_last_error()
+    # backward: workspace = lse_log2 + dpsum + fp32 dq_accum + deterministic-mode semaphores (two per 128-row query block)
+    bw = _lib.BwdArgs()
+    bw.dtype = _lib.BF16
+    for f in ("dout", "q", "k", "v", "out", "softmax_lse", "dq", "dk", "dv"):
+        setattr(bw, f, 16)
+    bw.b, bw.seqlen_q, bw.seqlen_k, bw.h, bw.h_k, bw.d = 2, 1000, 700, 6, 2, 128
+    ws = fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw))
+    sq_r = 1024
+    stat = 2 * 6 * sq_r * 4
+    assert ws >= 2 * stat + stat * 128 + 2 * 6 * (sq_r // 128) * 2 * 4
+    bw.d = 192
+    assert fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw)) == 0 and b"at most 128" in fa_lib.fa_b200_last_error()
+    bw.d, bw.p_dropout, bw.softcap = 128, 0.2, 10.0
+    assert fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw)) == 0 and b"dropout" in fa_lib.fa_b200_last_error()
+    # pitched-copy helper rejects an unknown direction before touching CUDA
+    assert fa_lib.fa_b200_memcpy2d_async(16, 64, 32, 64, 64, 1, 7, None) != 0 and b"kind" in fa_lib.fa_b200_last_error()
