@@ -9,6 +9,7 @@
 
 #include "../../include/fa_b200.h"
 #include "fa_api_common.h"
+#include "fa_bwd256_sm100.cuh"
 #include "fa_bwd2_sm100.cuh"
 #include "fa_bwd_sm100.cuh"
 
@@ -22,6 +23,13 @@ struct BwdPlan {
   size_t off_lse, off_dps, off_dq, off_sem, total;
 };
 
+// head dims 129..256 run fa_bwd256_kernel (fa_bwd256_sm100.cuh); FA_B200_BWD_HD256=0 restores the round-1 behaviour
+// of rejecting them
+static bool hd256_enabled() {
+  static int mode = [] { const char* e = getenv("FA_B200_BWD_HD256"); return e ? atoi(e) : 1; }();
+  return mode != 0;
+}
+
 static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   if (a.dtype != FA_B200_FP16 && a.dtype != FA_B200_BF16) return set_error("FlashAttention only support fp16 and bf16 data type");
   if (!a.dout || !a.q || !a.k || !a.v || !a.out || !a.softmax_lse || !a.dq || !a.dk || !a.dv)
@@ -29,13 +37,13 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   if (a.b <= 0) return set_error("batch size must be positive");
   if (a.d <= 0 || a.d > 256) return set_error("FlashAttention backward only supports head dimension at most 256");
   if (a.d % 8 != 0) return set_error("head_size should be a multiple of 8");
-  if (a.d > 128) return set_error("this build of fa_b200 supports head dimension at most 128");
+  if (a.d > 128 && !hd256_enabled()) return set_error("this build of fa_b200 supports head dimension at most 128");
   if (a.p_dropout < 0.f || a.p_dropout >= 1.f) return set_error("p_dropout must be in [0, 1)");
   if (a.p_dropout > 0.f && a.softcap > 0.f) return set_error("Softcapping does not support dropout for now");
   if (a.h <= 0 || a.h_k <= 0 || a.h % a.h_k != 0)
     return set_error("Number of heads in key/value must divide number of heads in query");
   if (varlen && (!a.cu_seqlens_q || !a.cu_seqlens_k)) return set_error("cu_seqlens_q and cu_seqlens_k are required");
-  pl->kD = a.d <= 64 ? 64 : 128;
+  pl->kD = a.d <= 64 ? 64 : (a.d <= 128 ? 128 : 256);
   pl->sq_r = (a.seqlen_q + 127) / 128 * 128;
   int wl = a.window_size_left, wr = a.window_size_right;
   if (wl >= a.seqlen_k) wl = -1;
@@ -47,8 +55,9 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   pl->off_dps = align256(stat);
   pl->off_dq = pl->off_dps + align256(stat);
   pl->off_sem = pl->off_dq + align256(stat * pl->kD);   // deterministic mode: one counter per (b, h, query block),
-  pl->total = pl->off_sem + align256(stat / 128 * 2);    // placed right behind dq_accum so one memset clears both
-                                                          // (x2: the CTA-pair kernel orders each query half separately)
+  pl->total = pl->off_sem + align256(stat / 128 * (pl->kD == 256 ? 4 : 2));   // placed right behind dq_accum so one
+                          // memset clears both (x2: the CTA-pair kernel orders each query half separately; x4: the
+                          // head-dim 256 kernel has one chain per 64-query tile and output half)
   return 0;
 }
 
@@ -92,6 +101,24 @@ static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t st
   return 0;
 }
 
+// head dims 129..256 (fa_bwd256_sm100.cuh): two CTAs (output halves) per key block
+template <typename T, bool kSoftcap, bool kDropout>
+static int launch_bwd_hd256(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = fa_bwd256_kernel<T, kSoftcap, kDropout>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd256Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(bwd256): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  grid.x *= 2;
+  kern<<<grid, Bwd256Cfg::kThreads, Bwd256Cfg::kSmemBytes, stream>>>(kp);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_bwd256_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 static bool use_pair_kernel(int kD) {
   // default on: measured 1125-1239 vs 1000-1084 TFLOP/s (bwd, b4 h16 s8192 d128); FA_B200_BWD_PAIR=0 selects fa_bwd_kernel
   static int mode = [] { const char* e = getenv("FA_B200_BWD_PAIR"); return e ? atoi(e) : 1; }();
@@ -109,7 +136,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   // semaphores (and the fp16-accumulator experiment build) still need a memset
   cudaError_t e = cudaSuccess;
   float* clear_rows = dq_accum;
-  if (FA_BWD_DQ_FP16) {
+  if (FA_BWD_DQ_FP16 || kD == 256) {   // (the preprocess kernel clears 128 columns per row)
     clear_rows = nullptr;
     e = cudaMemsetAsync(dq_accum, 0, pl.total - pl.off_dq, stream);
   } else if (a.deterministic) {
@@ -150,7 +177,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
                            dq_accum, dims, str, box)) return rc;
   }
   const bool pair = use_pair_kernel(kD);
-  if (pair) {
+  if (pair || kD == 256) {
     auto map64 = [&](CUtensorMap* tm, const void* base, int64_t bs, int64_t rs, int64_t hs, int rows_dense, int rows_varlen,
                      int heads) -> int {
       uint64_t rows = varlen ? rows_varlen : rows_dense, nb = varlen ? 1 : a.b;
@@ -179,6 +206,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   kp.alibi_slopes = a.alibi_slopes; kp.alibi_batch_stride = a.alibi_slopes_batch_stride;
   kp.b = a.b; kp.h = a.h; kp.h_k = a.h_k; kp.sq = a.seqlen_q; kp.sk = a.seqlen_k; kp.d = a.d; kp.g = a.h / a.h_k;
   kp.sq_r = sq_r;
+  kp.dq_accum = dq_accum;
   kp.has_left = pl.has_left; kp.has_right = pl.has_right; kp.wl = pl.wl; kp.wr = pl.wr;
   kp.scale = a.softmax_scale;
   if (a.softcap > 0.f) { kp.softcap_pre = a.softmax_scale / a.softcap; kp.scale_eff = a.softcap; }
@@ -200,9 +228,18 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
       launched = true;
     }
   }
-  if (!launched) {
-    if (a.p_dropout > 0.f) rc = launch_bwd_main<T, kD, false, true>(kp, grid, stream);
-    else rc = a.softcap > 0.f ? launch_bwd_main<T, kD, true>(kp, grid, stream) : launch_bwd_main<T, kD, false>(kp, grid, stream);
+  if constexpr (kD == 256) {
+    kp.sched_lpt = 0;
+    rc = a.p_dropout > 0.f ? launch_bwd_hd256<T, false, true>(kp, grid, stream)
+       : a.softcap > 0.f ? launch_bwd_hd256<T, true, false>(kp, grid, stream)
+                         : launch_bwd_hd256<T, false, false>(kp, grid, stream);
+    launched = true;
+  }
+  if constexpr (kD != 256) {
+    if (!launched) {
+      if (a.p_dropout > 0.f) rc = launch_bwd_main<T, kD, false, true>(kp, grid, stream);
+      else rc = a.softcap > 0.f ? launch_bwd_main<T, kD, true>(kp, grid, stream) : launch_bwd_main<T, kD, false>(kp, grid, stream);
+    }
   }
   if (rc) return rc;
   {
@@ -223,8 +260,12 @@ static int run_bwd(const fa_b200_bwd_args& a, bool varlen, cudaStream_t stream) 
   if (reinterpret_cast<uintptr_t>(a.workspace) % 256 != 0) return set_error("backward workspace must be 256-byte aligned");
   if (a.seqlen_q == 0 || a.seqlen_k == 0) return 0;
   if (a.dtype == FA_B200_BF16)
-    return pl.kD == 64 ? run_bwd_typed<__nv_bfloat16, 64>(a, pl, varlen, stream) : run_bwd_typed<__nv_bfloat16, 128>(a, pl, varlen, stream);
-  return pl.kD == 64 ? run_bwd_typed<__half, 64>(a, pl, varlen, stream) : run_bwd_typed<__half, 128>(a, pl, varlen, stream);
+    return pl.kD == 64    ? run_bwd_typed<__nv_bfloat16, 64>(a, pl, varlen, stream)
+           : pl.kD == 128 ? run_bwd_typed<__nv_bfloat16, 128>(a, pl, varlen, stream)
+                          : run_bwd_typed<__nv_bfloat16, 256>(a, pl, varlen, stream);
+  return pl.kD == 64    ? run_bwd_typed<__half, 64>(a, pl, varlen, stream)
+         : pl.kD == 128 ? run_bwd_typed<__half, 128>(a, pl, varlen, stream)
+                        : run_bwd_typed<__half, 256>(a, pl, varlen, stream);
 }
 
 }  // namespace fa

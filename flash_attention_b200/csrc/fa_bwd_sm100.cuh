@@ -57,6 +57,7 @@ struct BwdKernelParams {
   int sched_lpt;              // key block (pair) index is the slowest grid dimension: heavy (masked) work first
   DropoutParams drop;         // kDropout kernels only: the forward's rng_state and p_dropout
   const uint64_t* rng_state;  // device copy of {seed, offset}; overrides drop.seed/off when non-null
+  float* dq_accum;            // fa_bwd256_kernel only (adds its dQ partials with red.global instead of TMA): (b, h, sq_r, 256)
 };
 
 #ifndef FA_BWD_DQ_FP16

@@ -40,6 +40,17 @@ CASES = [
     (2, 300, 300, 8, 2, 128, True, (-1, -1), 0.0, torch.bfloat16),    # GQA: dK/dV accumulate over the group in-kernel
     (1, 130, 257, 2, 2, 40, True, (-1, -1), 0.0, torch.bfloat16),
     (1, 200, 200, 2, 2, 96, False, (-1, -1), 0.0, torch.float16),
+    # head dims 129..256: fa_bwd256_kernel (64-query tiles, output head dim split over two CTAs)
+    (1, 64, 128, 1, 1, 256, False, (-1, -1), 0.0, torch.bfloat16),
+    (2, 256, 384, 2, 2, 256, False, (-1, -1), 0.0, torch.float16),
+    (2, 113, 203, 3, 3, 256, True, (-1, -1), 0.0, torch.bfloat16),
+    (2, 113, 203, 3, 3, 192, False, (-1, -1), 0.0, torch.float16),
+    (1, 1023, 1024, 2, 1, 192, True, (-1, -1), 0.0, torch.bfloat16),
+    (1, 512, 256, 2, 2, 256, True, (-1, -1), 0.0, torch.bfloat16),    # key blocks with no queries
+    (1, 384, 500, 4, 2, 224, False, (100, 37), 0.0, torch.bfloat16),
+    (1, 700, 700, 1, 1, 160, True, (129, -1), 0.0, torch.bfloat16),
+    (1, 256, 256, 2, 2, 256, False, (-1, -1), 15.0, torch.bfloat16),
+    (2, 300, 300, 8, 2, 136, True, (-1, -1), 0.0, torch.bfloat16),
 ]
 
 
@@ -56,10 +67,11 @@ def test_backward_matches_oracle(fab, b, sq, sk, h, hk, d, causal, window, softc
         assert err <= bound, f"{name}: {err:.3e} > {bound:.3e}"
 
 
+@pytest.mark.parametrize("d", [128, 256])
 @pytest.mark.parametrize("causal", [False, True])
-def test_backward_alibi(fab, causal):
+def test_backward_alibi(fab, causal, d):
     b, sq, sk, h = 2, 200, 333, 4
-    q, k, v = make_qkv(b, sq, sk, h, h, 128)
+    q, k, v = make_qkv(b, sq, sk, h, h, d)
     do = torch.randn_like(q)
     sl = (torch.rand(b, h, device="cuda") * 0.3).float()
     dq, dk, dv = _grads(fab, q, k, v, do, causal=causal, alibi_slopes=sl)
@@ -69,11 +81,12 @@ def test_backward_alibi(fab, causal):
         assert (g.float().cpu() - ref).abs().max().item() <= bound, name
 
 
-def test_varlen_backward(fab):
+@pytest.mark.parametrize("d", [128, 192])
+def test_varlen_backward(fab, d):
     from oracle.attention_oracle import attention_oracle_bwd
 
     torch.manual_seed(0)
-    h, hk, d = 4, 2, 128
+    h, hk = 4, 2
     lens_q, lens_k = [37, 256, 1, 300], [100, 256, 513, 300]
     cu_q = torch.tensor([0] + list(torch.tensor(lens_q).cumsum(0)), dtype=torch.int32, device="cuda")
     cu_k = torch.tensor([0] + list(torch.tensor(lens_k).cumsum(0)), dtype=torch.int32, device="cuda")
@@ -122,11 +135,12 @@ def test_full_size_slice_vs_oracle(fab):
     assert (dq[bi:bi + 1, :n, hi:hi + 1].float().cpu() - rdq).abs().max().item() <= 3e-2 * max(1.0, rdq.abs().max().item())
 
 
+@pytest.mark.parametrize("d", [128, 256])
 @pytest.mark.parametrize("causal,window", [(False, (-1, -1)), (True, (-1, -1)), (False, (200, 100))])
-def test_deterministic_backward_is_bitwise_reproducible(fab, causal, window):
+def test_deterministic_backward_is_bitwise_reproducible(fab, causal, window, d):
     """deterministic=True orders the dQ reduce-adds (reference: test_flash_attn_deterministic,
     tests/test_flash_attn.py:2413-2438: repeated runs must be torch.equal)."""
-    b, sq, sk, h, hk, d = 2, 640, 900, 4, 2, 128
+    b, sq, sk, h, hk = 2, 640, 900, 4, 2
     q, k, v = make_qkv(b, sq, sk, h, hk, d)
     do = torch.randn(b, sq, h, d, device="cuda", dtype=torch.bfloat16)
     g0 = _grads(fab, q, k, v, do, causal=causal, window=window, deterministic=True)

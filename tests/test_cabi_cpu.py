@@ -122,8 +122,12 @@ def test_dropout_and_backward_argument_checks_without_gpu(fa_lib):
     sq_r = 1024
     stat = 2 * 6 * sq_r * 4
     assert ws >= 2 * stat + stat * 128 + 2 * 6 * (sq_r // 128) * 2 * 4
+    # head dims 129..256: fp32 dq_accum rows of 256 columns, one semaphore chain per (64-query tile, output half)
     bw.d = 192
-    assert fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw)) == 0 and b"at most 128" in fa_lib.fa_b200_last_error()
+    ws = fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw))
+    assert ws >= 2 * stat + stat * 256 + 2 * 6 * (sq_r // 64) * 2 * 4
+    bw.d = 264
+    assert fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw)) == 0 and b"at most 256" in fa_lib.fa_b200_last_error()
     bw.d, bw.p_dropout, bw.softcap = 128, 0.2, 10.0
     assert fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw)) == 0 and b"dropout" in fa_lib.fa_b200_last_error()
     # pitched-copy helper rejects an unknown direction before touching CUDA

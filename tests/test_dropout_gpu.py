@@ -36,6 +36,8 @@ CASES = [
     (1, 384, 500, 4, 2, 128, False, (100, 37), 0.3, torch.bfloat16),
     (1, 300, 300, 8, 2, 96, True, (-1, -1), 0.05, torch.bfloat16),
     (1, 257, 130, 2, 2, 40, True, (-1, -1), 0.5, torch.bfloat16),
+    (1, 300, 421, 4, 2, 256, True, (-1, -1), 0.2, torch.bfloat16),     # head-dim 256 backward kernel
+    (2, 200, 200, 2, 2, 192, False, (64, 64), 0.1, torch.float16),
 ]
 
 

@@ -62,11 +62,7 @@ def test_varlen_matrix_sample(i, d, sq, sk, mha, causal, local, alibi, p, det, m
     torch.cuda.manual_seed(i)
     out, lse, s_dmask = fab.flash_attn_varlen_func(q, k, v, cu_q, cu_k, max(lq), max(lk), p, causal=causal, window_size=window,
                                                    alibi_slopes=slopes, deterministic=det, return_attn_probs=True)
-    if d <= 128:
-        out.backward(do)
-    else:
-        with pytest.raises(RuntimeError, match="head dimension at most 128"):
-            out.backward(do)
+    out.backward(do)
     for j in range(b):
         qs, ks = slice(int(cu_q[j]), int(cu_q[j + 1])), slice(int(cu_k[j]), int(cu_k[j + 1]))
         kw = dict(causal=causal, window=window, alibi_slopes=slopes[j:j + 1] if slopes is not None else None)
@@ -81,9 +77,8 @@ def test_varlen_matrix_sample(i, d, sq, sk, mha, causal, local, alibi, p, det, m
         assert torch.equal(torch.isfinite(lj), fin)
         if fin.any():
             assert (lj[fin] - lse_ref[fin]).abs().max().item() <= 2e-3 * max(1.0, lse_ref[fin].abs().max().item())
-        if d <= 128:
-            tol = bwd_tolerances(qj, kj, vj, do[qs][None], **kw)
-            for name, gt in (("dq", q.grad[qs]), ("dk", k.grad[ks]), ("dv", v.grad[ks])):
-                ref, bnd = tol[name]
-                e = (gt[None].float().cpu() - ref).abs().max().item()
-                assert not torch.isnan(gt).any() and e <= bnd, f"seq {j} {name}: {e:.3e} > {bnd:.3e}"
+        tol = bwd_tolerances(qj, kj, vj, do[qs][None], **kw)
+        for name, gt in (("dq", q.grad[qs]), ("dk", k.grad[ks]), ("dv", v.grad[ks])):
+            ref, bnd = tol[name]
+            e = (gt[None].float().cpu() - ref).abs().max().item()
+            assert not torch.isnan(gt).any() and e <= bnd, f"seq {j} {name}: {e:.3e} > {bnd:.3e}"
