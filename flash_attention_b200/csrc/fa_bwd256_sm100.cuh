@@ -16,7 +16,8 @@
 //   dQ_c^T = K[:, c]^T dS^T     SS  M=128 N=64  K=128   -> TMEM [128,192)   (lane = head-dim column, column = query)
 //   dQ_c^T -> registers -> red.global.add.f32 into dq_accum (a warp adds 32 consecutive floats of one query row)
 //
-// Shared memory 209 KB: K, V (4 panels of 64 columns x 128 rows each), Q, dO (4 panels x 64 rows, single stage), dS^T.
+// Shared memory 225 KB: K, V (4 panels of 64 columns x 128 rows each), Q (4 panels x 64 rows; the two panels of this
+// CTA's output half double-buffered), dO (single stage), dS^T.
 // Warps as in fa_bwd_kernel: 0-7 compute (key-row quadrant w%4, query half w/4), 8-11 dQ drain, 12 MMA issuer, 13 TMA.
 #pragma once
 #include "fa_bwd_sm100.cuh"
@@ -31,10 +32,14 @@ struct Bwd256Cfg {
   static constexpr int kQPanel = 64 * 128;            // Q / dO panel: 64 query rows x 128 B
   static constexpr int kSK = 0;
   static constexpr int kSV = kSK + kPanelsD * kKPanel;
-  static constexpr int kSQ = kSV + kPanelsD * kKPanel;
-  static constexpr int kSDO = kSQ + kPanelsD * kQPanel;
+  // Q: the two panels of the OTHER output half are dead once S^T has been computed, the two panels of this CTA's half
+  // are also the B operand of dK -> own-half panels double-buffered, so that the next tile's Q can be loaded as soon
+  // as S^T of this tile is done (a single-stage Q exposed the whole load latency every tile: 528 TFLOP/s)
+  static constexpr int kSQo = kSV + kPanelsD * kKPanel;    // other half: 2 panels, 1 stage
+  static constexpr int kSQc = kSQo + 2 * kQPanel;          // own half:   2 panels x 2 stages
+  static constexpr int kSDO = kSQc + 4 * kQPanel;
   static constexpr int kSDS = kSDO + kPanelsD * kQPanel;   // 128 keys x 64 queries, 16-bit
-  static constexpr int kSStat = kSDS + kKPanel;            // lse_log2[64], dpsum[64]
+  static constexpr int kSStat = kSDS + kKPanel;            // 2 stages x (lse_log2[64], dpsum[64])
   static constexpr int kSBar = kSStat + 1024;
   static constexpr int kNumBars = 16;
   static constexpr int kSmemBytes = kSBar + 8 * kNumBars + 16;
@@ -71,10 +76,11 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();
   uint8_t* smem_gen = smem_raw;
-  const uint32_t sK = smem_base + Cfg::kSK, sV = smem_base + Cfg::kSV, sQ = smem_base + Cfg::kSQ;
+  const uint32_t sK = smem_base + Cfg::kSK, sV = smem_base + Cfg::kSV;
+  const uint32_t sQo = smem_base + Cfg::kSQo, sQc = smem_base + Cfg::kSQc;
   const uint32_t sDO = smem_base + Cfg::kSDO, sDS = smem_base + Cfg::kSDS;
   const uint32_t sStat = smem_base + Cfg::kSStat, sBar = smem_base + Cfg::kSBar;
-  enum { B_KV = 0, B_QF, B_QE, B_DOF, B_DOE, B_SF, B_DPF, B_PF, B_DSF, B_DQF, B_DQE, B_DKV };
+  enum { B_KV = 0, B_QF0, B_QF1, B_QEO, B_QEC0, B_QEC1, B_DOF, B_DOE, B_SF, B_DPF, B_PF, B_DSF, B_DQF, B_DQE, B_DKV };
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSBar + 8 * Cfg::kNumBars);
@@ -86,7 +92,8 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
   if (warp == 12) {
     if (lane == 0) {
       mbar_init(bar(B_KV), 1);
-      mbar_init(bar(B_QF), 1); mbar_init(bar(B_QE), 1);
+      mbar_init(bar(B_QF0), 1); mbar_init(bar(B_QF1), 1);
+      mbar_init(bar(B_QEO), 1); mbar_init(bar(B_QEC0), 1); mbar_init(bar(B_QEC1), 1);
       mbar_init(bar(B_DOF), 1); mbar_init(bar(B_DOE), 1);
       mbar_init(bar(B_SF), 1); mbar_init(bar(B_DPF), 1);
       mbar_init(bar(B_PF), 8); mbar_init(bar(B_DSF), 8);
@@ -120,13 +127,17 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
           const int hq = hk * p.g + it / n_m;
           const int m = m_min + it % n_m;
           const int64_t srow = (int64_t(bidb) * p.h + hq) * p.sq_r + m * 64;
-          mbar_wait(bar(B_QE), (it & 1) ^ 1, 400);
-          mbar_arrive_expect_tx(bar(B_QF), Cfg::kPanelsD * Cfg::kQPanel + 512);
+          const int st = it & 1;
+          mbar_wait(bar(B_QEO), (it & 1) ^ 1, 400);                  // S^T of tile it-1 done
+          mbar_wait(bar(B_QEC0 + st), ((it >> 1) & 1) ^ 1, 401);     // dK of tile it-2 done
+          mbar_arrive_expect_tx(bar(B_QF0 + st), Cfg::kPanelsD * Cfg::kQPanel + 512);
 #pragma unroll
-          for (int pn = 0; pn < Cfg::kPanelsD; ++pn)
-            tma_load_4d(sQ + pn * Cfg::kQPanel, &p.tm_q64, bar(B_QF), pn * 64, q_off + m * 64, hq, bq);
-          bulk_load_1d(sStat, p.lse_log2 + srow, 256, bar(B_QF));
-          bulk_load_1d(sStat + 256, p.dpsum + srow, 256, bar(B_QF));
+          for (int pn = 0; pn < Cfg::kPanelsD; ++pn) {
+            const uint32_t dst = ((pn >> 1) == chalf ? sQc + st * 2 * Cfg::kQPanel : sQo) + (pn & 1) * Cfg::kQPanel;
+            tma_load_4d(dst, &p.tm_q64, bar(B_QF0 + st), pn * 64, q_off + m * 64, hq, bq);
+          }
+          bulk_load_1d(sStat + st * 512, p.lse_log2 + srow, 256, bar(B_QF0 + st));
+          bulk_load_1d(sStat + st * 512 + 256, p.dpsum + srow, 256, bar(B_QF0 + st));
           mbar_wait(bar(B_DOE), (it & 1) ^ 1, 410);
           mbar_arrive_expect_tx(bar(B_DOF), Cfg::kPanelsD * Cfg::kQPanel);
 #pragma unroll
@@ -148,19 +159,22 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
         constexpr uint64_t d_mn_q = smem_desc_sw128(Cfg::kQPanel, 1024);   // MN-major view of 64-row panels (Q, dO)
         auto lo = [](uint64_t base, uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | uint32_t(base); };
         auto mk = [](uint64_t base, uint32_t lo32) { return (base & 0xFFFFFFFF00000000ull) | lo32; };
-        // D = A B^T over the full head dim: A = 128-row panels (K or V), B = 64-row panels (Q or dO)
-        auto mma_full_d = [&](uint32_t d_t, uint32_t a0, uint32_t b0) {
-          const uint32_t la = lo(d_kmaj, a0), lb = lo(d_kmaj, b0);
+        // D = A B^T over the full head dim: A = 128-row panels (K or V); B = 64-row panels: panels of this CTA's output
+        // half start at b_own, the other two at b_oth (dO: one contiguous tile, Q: split buffers)
+        auto mma_full_d = [&](uint32_t d_t, uint32_t a0, uint32_t b_own, uint32_t b_oth) {
+          const uint32_t la = lo(d_kmaj, a0), lown = lo(d_kmaj, b_own), loth = lo(d_kmaj, b_oth);
 #pragma unroll
           for (int kk = 0; kk < 16; ++kk) {
-            const uint32_t offa = ((kk / 4) * Cfg::kKPanel + (kk % 4) * 32) >> 4;
-            const uint32_t offb = ((kk / 4) * Cfg::kQPanel + (kk % 4) * 32) >> 4;
-            mma_ss<false>(d_t, mk(d_kmaj, la + offa), mk(d_kmaj, lb + offb), id_s, kk > 0);
+            const int pn = kk / 4;
+            const uint32_t offa = (pn * Cfg::kKPanel + (kk % 4) * 32) >> 4;
+            const uint32_t offb = ((pn & 1) * Cfg::kQPanel + (kk % 4) * 32) >> 4;
+            mma_ss<false>(d_t, mk(d_kmaj, la + offa), mk(d_kmaj, ((pn >> 1) == chalf ? lown : loth) + offb), id_s, kk > 0);
           }
         };
+        const uint32_t sDOown = sDO + 2 * chalf * Cfg::kQPanel, sDOoth = sDO + 2 * (chalf ^ 1) * Cfg::kQPanel;
         // D (+)= A[tmem, 64 queries packed] * B[64 query rows x 128 head-dim columns of this half, MN-major]
-        auto mma_out = [&](uint32_t d_t, uint32_t a_t, uint32_t b0, bool acc) {
-          const uint32_t lb = lo(d_mn_q, b0 + 2 * chalf * Cfg::kQPanel);
+        auto mma_out = [&](uint32_t d_t, uint32_t a_t, uint32_t b_own, bool acc) {
+          const uint32_t lb = lo(d_mn_q, b_own);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             mma_ts<false>(d_t, a_t + (kk >> 1) * 32 + (kk & 1) * 8, mk(d_mn_q, lb + kk * (2048 >> 4)), id_dkv,
@@ -168,24 +182,26 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
         };
         const uint32_t lo_kt = lo(d_mn_k, sK + 2 * chalf * Cfg::kKPanel), lo_ds = lo(d_mn_k, sDS);
         mbar_wait(bar(B_KV), 0, 500);
-        mbar_wait(bar(B_QF), 0, 501);
+        mbar_wait(bar(B_QF0), 0, 501);
         tc_fence_after();
-        mma_full_d(tS, sK, sQ);
+        mma_full_d(tS, sK, sQc, sQo);
         mma_commit(bar(B_SF));
+        mma_commit(bar(B_QEO));
         mbar_wait(bar(B_DOF), 0, 502);
         tc_fence_after();
-        mma_full_d(tDP, sV, sDO);
+        mma_full_d(tDP, sV, sDOown, sDOoth);
         mma_commit(bar(B_DPF));
         for (int it = 0; it < n_iter; ++it) {
           const uint32_t ph = it & 1;
           mbar_wait(bar(B_PF), ph, 510);
           tc_fence_after();
-          mma_out(tDV, tS, sDO, it > 0);
+          const int st = it & 1;
+          mma_out(tDV, tS, sDOown, it > 0);
           mma_commit(bar(B_DOE));
           mbar_wait(bar(B_DSF), ph, 511);
           tc_fence_after();
-          mma_out(tDK, tS + 16, sQ, it > 0);
-          mma_commit(bar(B_QE));
+          mma_out(tDK, tS + 16, sQc + st * 2 * Cfg::kQPanel, it > 0);
+          mma_commit(bar(B_QEC0 + st));
           if (it > 0) {
             mbar_wait(bar(B_DQE), ph ^ 1, 512);   // dQ^T of the previous tile has been read out of TMEM [128,192)
             tc_fence_after();
@@ -195,13 +211,15 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
             mma_ss<false>(tDQ, mk(d_mn_k, lo_kt + kk * (2048 >> 4)), mk(d_mn_k, lo_ds + kk * (2048 >> 4)), id_dq, kk > 0);
           mma_commit(bar(B_DQF));
           if (it + 1 < n_iter) {
-            mbar_wait(bar(B_QF), ph ^ 1, 513);
+            const int st1 = st ^ 1;
+            mbar_wait(bar(B_QF0 + st1), ((it + 1) >> 1) & 1, 513);
             tc_fence_after();
-            mma_full_d(tS, sK, sQ);
+            mma_full_d(tS, sK, sQc + st1 * 2 * Cfg::kQPanel, sQo);
             mma_commit(bar(B_SF));
+            mma_commit(bar(B_QEO));
             mbar_wait(bar(B_DOF), ph ^ 1, 514);
             tc_fence_after();
-            mma_full_d(tDP, sV, sDO);
+            mma_full_d(tDP, sV, sDOown, sDOoth);
             mma_commit(bar(B_DPF));
           }
         }
@@ -295,17 +313,18 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
       const int q0 = m * 64 + hf * 32;
       float slope = 0.f;
       if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + hq] / p.scale_eff;
-      mbar_wait(bar(B_QF), it & 1, 700);
+      const int st = it & 1;
+      mbar_wait(bar(B_QF0 + st), (it >> 1) & 1, 700);   // lse_log2 / dpsum of this stage are in shared memory
       mbar_wait(bar(B_SF), it & 1, 701);
       tc_fence_after();
       uint32_t su[32];
       tmem_ld_x32(t_s, su);
       tmem_wait_ld();
       float* s = reinterpret_cast<float*>(su);
-      // lse_log2 / dpsum of this tile stay valid in shared memory for the whole iteration: the next Q load (which refills
-      // them) waits for dK of this tile, which is issued only after every compute warp has arrived on B_DSF
-      const float* s_lse = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat) + hf * 32;
-      const float* s_dps = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + 256) + hf * 32;
+      // this stage is refilled by the load of tile it+2, which waits for dK of this tile, which is issued only after
+      // every compute warp has arrived on B_DSF: the statistics stay valid for the whole iteration
+      const float* s_lse = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + st * 512) + hf * 32;
+      const float* s_dps = reinterpret_cast<const float*>(smem_gen + Cfg::kSStat + st * 512 + 256) + hf * 32;
       const float rel0 = float(q0 + shift - j);
       if constexpr (kSoftcap) {
 #pragma unroll
