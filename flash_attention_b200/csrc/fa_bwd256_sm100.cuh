@@ -152,7 +152,12 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
       if (n_iter > 0 && elect_one()) {
         constexpr uint32_t fmt = Elt<T>::kFmt;
         constexpr uint32_t id_s = make_idesc(fmt, fmt, 0, 0, 128, 64);     // S^T, dP^T : K-major A and B
-        constexpr uint32_t id_dkv = make_idesc(fmt, fmt, 0, 1, 128, 128);  // dV, dK    : A in TMEM, B MN-major
+        constexpr uint32_t id_dkv128 = make_idesc(fmt, fmt, 0, 1, 128, 128);  // dV, dK : A in TMEM, B MN-major
+        constexpr uint32_t id_dkv64 = make_idesc(fmt, fmt, 0, 1, 128, 64);
+        // head dims <= 192: the fourth 64-column panel is all zero-fill -> skip its 4 k-steps of S^T / dP^T, and the
+        // upper output half only has 64 live columns
+        const int nk = p.d <= 192 ? 12 : 16;
+        const uint32_t id_dkv = (chalf == 1 && p.d <= 192) ? id_dkv64 : id_dkv128;
         constexpr uint32_t id_dq = make_idesc(fmt, fmt, 1, 1, 128, 64);    // dQ^T      : A and B MN-major
         constexpr uint64_t d_kmaj = smem_desc_sw128(16, 1024);
         constexpr uint64_t d_mn_k = smem_desc_sw128(Cfg::kKPanel, 1024);   // MN-major view of 128-row panels (K, dS^T)
@@ -168,7 +173,8 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
             const int pn = kk / 4;
             const uint32_t offa = (pn * Cfg::kKPanel + (kk % 4) * 32) >> 4;
             const uint32_t offb = ((pn & 1) * Cfg::kQPanel + (kk % 4) * 32) >> 4;
-            mma_ss<false>(d_t, mk(d_kmaj, la + offa), mk(d_kmaj, ((pn >> 1) == chalf ? lown : loth) + offb), id_s, kk > 0);
+            if (kk < nk)
+              mma_ss<false>(d_t, mk(d_kmaj, la + offa), mk(d_kmaj, ((pn >> 1) == chalf ? lown : loth) + offb), id_s, kk > 0);
           }
         };
         const uint32_t sDOown = sDO + 2 * chalf * Cfg::kQPanel, sDOoth = sDO + 2 * (chalf ^ 1) * Cfg::kQPanel;

@@ -10,8 +10,10 @@
 // Main loop, everything transposed so that the resident K/V block is the MMA M operand (TMEM lane = key):
 //   S^T  = K Q^T            SS   -> TMEM [0,128)
 //   dP^T = V dO^T           SS   -> TMEM [128,256)
-//   P^T  = exp2(S^T*c - lse_log2[q])      compute warps, fp32 -> 16-bit into TMEM [0,64)
-//   dS^T = P^T * (dP^T - D[q])            compute warps -> TMEM [64,128) and shared memory (swizzled)
+//   P^T  = exp2(S^T*c - lse_log2[q])      compute warps, fp32 -> 16-bit into TMEM [0,32) + [64,96)
+//   dS^T = P^T * (dP^T - D[q])            compute warps -> TMEM [32,64) + [96,128) and shared memory (swizzled)
+//                                         (each warp packs into its OWN 64 S^T columns, so it can never overwrite
+//                                         columns that the warp of the other query half has not read yet)
 //   dV  += P^T dO           TS   -> TMEM [256,384)      (A = P^T from TMEM, B = dO as MN-major)
 //   dK  += dS^T Q           TS   -> TMEM [384,512)
 //   dQ   = dS K             SS   -> TMEM [128,256)      (A = dS^T tile as MN-major, B = K as MN-major)
@@ -332,8 +334,9 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
         auto mma_ts_mn = [&](uint32_t d_t, uint32_t a_t, uint32_t b0, bool acc) {
           const uint32_t lb = lo_mn(b0);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            mma_ts<false>(d_t, a_t + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), id_dkv, (acc || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk)   // 16 queries = 8 packed columns; query half h lives at columns 64 h
+            mma_ts<false>(d_t, a_t + (kk >> 2) * 64 + (kk & 3) * 8, mk(hi_mn, lb + kk * (2048 >> 4)), id_dkv,
+                          (acc || kk > 0) ? 1u : 0u);
         };
         const uint32_t lo_ds = lo_mn(sDS), lo_kmn = lo_mn(sK);
         mbar_wait(bar(B_KV), 0, 500);
@@ -354,7 +357,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
           mma_commit(bar(B_DOE));
           mbar_wait(bar(B_DSF), ph, 511);
           tc_fence_after();
-          mma_ts_mn(tDK, tS + 64, sQ + st * Cfg::kTileBytes, it > 0);
+          mma_ts_mn(tDK, tS + 32, sQ + st * Cfg::kTileBytes, it > 0);
           mma_commit(bar(B_QE0 + st));
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
@@ -481,8 +484,8 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
     const uint32_t lane_sel = uint32_t(wq * 32) << 16;
     const uint32_t t_s = tS + lane_sel + hf * 64;       // my 64 S^T columns
     const uint32_t t_dp = tDP + lane_sel + hf * 64;
-    const uint32_t t_p = tS + lane_sel + hf * 32;       // P^T  packed: 32 columns
-    const uint32_t t_ds = tS + lane_sel + 64 + hf * 32; // dS^T packed
+    const uint32_t t_p = t_s;                           // P^T  packed: 32 columns inside my own S^T columns
+    const uint32_t t_ds = t_s + 32;                     // dS^T packed: the other 32
     const float scale_log2 = p.scale_log2;
     // visible queries for this key: i in [i_lo, i_hi]
     const int i_lo = p.has_right ? j - shift - p.wr : -(1 << 30);

@@ -30,6 +30,8 @@ def run(tag, fn):
 if __name__ == "__main__":
     import flash_attention_b200 as fab
     run("fa_b200", fab.flash_attn_func)
+    if len(sys.argv) > 1 and sys.argv[1] == "ours":
+        sys.exit(0)
     try:
         from flash_attn import flash_attn_func
         run("FA2-2.8.3", flash_attn_func)
