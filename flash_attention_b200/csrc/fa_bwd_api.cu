@@ -133,10 +133,10 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   float* dq_accum = reinterpret_cast<float*>(ws + pl.off_dq);
   const int sq_r = pl.sq_r;
   // dq_accum is cleared by the preprocess kernel (same pass that reads O / dO); only the deterministic-mode
-  // semaphores (and the fp16-accumulator experiment build) still need a memset
+  // semaphores (and the 256-column accumulator of the head-dim 129..256 kernel) still need a memset
   cudaError_t e = cudaSuccess;
   float* clear_rows = dq_accum;
-  if (FA_BWD_DQ_FP16 || kD == 256) {   // (the preprocess kernel clears 128 columns per row)
+  if (kD == 256) {   // (the preprocess kernel clears 128 columns per row)
     clear_rows = nullptr;
     e = cudaMemsetAsync(dq_accum, 0, pl.total - pl.off_dq, stream);
   } else if (a.deterministic) {
@@ -169,11 +169,11 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   if (int rc = map16(&kp.tm_k, a.k, a.k_batch_stride, a.k_row_stride, a.k_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
   if (int rc = map16(&kp.tm_v, a.v, a.v_batch_stride, a.v_row_stride, a.v_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
   {
-    constexpr uint64_t esz = FA_BWD_DQ_FP16 ? 2 : 4;
+    constexpr uint64_t esz = 4;
     uint64_t dims[4] = {uint64_t(kD), uint64_t(sq_r), uint64_t(a.h), uint64_t(a.b)};
     uint64_t str[3] = {uint64_t(kD) * esz, uint64_t(sq_r) * kD * esz, uint64_t(a.h) * sq_r * kD * esz};
     uint32_t box[4] = {uint32_t(128 / esz), 128, 1, 1};
-    if (int rc = make_tmap(&kp.tm_dq, FA_BWD_DQ_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+    if (int rc = make_tmap(&kp.tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                            dq_accum, dims, str, box)) return rc;
   }
   const bool pair = use_pair_kernel(kD);

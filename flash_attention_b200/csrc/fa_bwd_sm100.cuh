@@ -62,10 +62,6 @@ struct BwdKernelParams {
   float* dq_accum;            // fa_bwd256_kernel only (adds its dQ partials with red.global instead of TMA): (b, h, sq_r, 256)
 };
 
-#ifndef FA_BWD_DQ_FP16
-#define FA_BWD_DQ_FP16 0   // 1: accumulate dQ partials in fp16 (pre-scaled by softmax_scale) instead of fp32
-#endif
-
 template <int kD>
 struct BwdCfg {
   static constexpr int kThreads = 512;
@@ -177,20 +173,9 @@ __global__ void __launch_bounds__(256) fa_bwd_convert_dq(const float* __restrict
   if (cu_q) { q_off = cu_q[bidb]; sq_b = cu_q[bidb + 1] - q_off; }
   if (row >= sq_b) return;
   T* dst = dq + (cu_q ? 0 : bidb * dq_bs) + int64_t(q_off + row) * dq_rs + int64_t(head) * dq_hs;
-#if FA_BWD_DQ_FP16
-  const __half* src = reinterpret_cast<const __half*>(dq_accum) + ((int64_t(bidb) * h + head) * sq_r + row) * kD;
-  scale = 1.0f;  // already applied before the fp16 accumulation
-#else
   const float* src = dq_accum + ((int64_t(bidb) * h + head) * sq_r + row) * kD;
-#endif
   for (int c = lane * 4; c < d; c += 128) {
-#if FA_BWD_DQ_FP16
-    const uint2 hv = *reinterpret_cast<const uint2*>(src + c);
-    const __half2 h01 = *reinterpret_cast<const __half2*>(&hv.x), h23 = *reinterpret_cast<const __half2*>(&hv.y);
-    const float4 v = make_float4(__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23));
-#else
     const float4 v = *reinterpret_cast<const float4*>(src + c);
-#endif
     uint2 o;
     o.x = Elt<T>::pack(v.x * scale, v.y * scale);
     o.y = Elt<T>::pack(v.z * scale, v.w * scale);
@@ -424,29 +409,6 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(B_DQE));
         }
-#if FA_BWD_DQ_FP16
-        {
-          // experiment: dq_accum in fp16 -> one 128-byte row per 64 columns, half the TMA reduce traffic
-          const int buf = nbuf & 1;
-          if (leader && nbuf >= 2) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          uint8_t* dst = smem_gen + Cfg::kSDQ + buf * Cfg::kPanelBytes + r * 128;
-#pragma unroll
-          for (int x = 0; x < 8; ++x)
-            *reinterpret_cast<uint4*>(dst + ((x ^ (r & 7)) * 16)) =
-                make_uint4(pack_f16(__uint_as_float(v[8 * x]) * p.scale, __uint_as_float(v[8 * x + 1]) * p.scale),
-                           pack_f16(__uint_as_float(v[8 * x + 2]) * p.scale, __uint_as_float(v[8 * x + 3]) * p.scale),
-                           pack_f16(__uint_as_float(v[8 * x + 4]) * p.scale, __uint_as_float(v[8 * x + 5]) * p.scale),
-                           pack_f16(__uint_as_float(v[8 * x + 6]) * p.scale, __uint_as_float(v[8 * x + 7]) * p.scale));
-          fence_proxy_async();
-          named_bar_sync(2, 128);
-          if (leader) {
-            tma_reduce_add_4d(&p.tm_dq, sDQ + buf * Cfg::kPanelBytes, half * 64, m * 128, hq, bidb);
-            tma_store_commit();
-          }
-          ++nbuf;
-        }
-#else
 #pragma unroll
         for (int c = 0; c < 2; ++c, ++nbuf) {
           const int buf = nbuf & 1;
@@ -465,7 +427,6 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
             tma_store_commit();
           }
         }
-#endif
       }
       if (sem && leader) {  // all reduce-adds of this iteration have been performed: pass the turn on
         tma_store_wait<0>();
