@@ -1,5 +1,7 @@
 """Randomised stress of the backward (pair kernel by default): many small random shapes / masks, each run 3 times.
-Checks (a) the 3x oracle rule, (b) dK/dV bitwise repeatable always, dQ bitwise repeatable with deterministic=True."""
+Checks (a) the 3x oracle rule, (b) dK/dV bitwise repeatable always, dQ bitwise repeatable with deterministic=True.
+usage: stress_bwd.py [seed] [n_configs] [head dims, comma separated]   e.g. `stress_bwd.py 5 120 160,192,224,256`
+for the head-dim 129..256 kernel (the default list keeps the sequence that tests/test_bwd_stress_gpu.py pins)."""
 import os
 import random
 import sys
@@ -12,13 +14,14 @@ from tests.util import bwd_tolerances, make_qkv
 
 rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n_cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+head_dims = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [128, 128, 128, 96, 64]
 bad = 0
 for ci in range(n_cfg):
     b = rng.choice([1, 1, 2, 3])
     hk = rng.choice([1, 2, 3])
     g = rng.choice([1, 1, 2, 4])
     h = hk * g
-    d = rng.choice([128, 128, 128, 96, 64])
+    d = rng.choice(head_dims)
     sq = rng.choice([rng.randint(1, 300), rng.randint(300, 1400), 128 * rng.randint(1, 9), 256 * rng.randint(1, 5)])
     sk = rng.choice([sq, rng.randint(1, 1400), 128 * rng.randint(1, 10), 256 * rng.randint(1, 5) + rng.choice([0, 1, 127])])
     mode = rng.choice(["none", "causal", "local", "causal_local"])
