@@ -104,6 +104,7 @@ def cpu_baseline(causal, mode, budget_s=12.0):
     fl = 4.0 * pairs * d * (3.5 if mode == "fwd_bwd" else 1.0)
     fn = (lambda: attention_oracle_bwd(q, k, v, do, causal=causal)) if mode == "fwd_bwd" else (lambda: attention_oracle(q, k, v, causal=causal))
     fn()
+    _pick_cpu_threads(fn)
     t0, n = time.perf_counter(), 0
     while time.perf_counter() - t0 < budget_s and n < 50:
         fn()
@@ -113,11 +114,33 @@ def cpu_baseline(causal, mode, budget_s=12.0):
             "sample": f"fp32 attention_oracle {mode}, b=1 h=1 last {rows} query rows x {s} keys d={d}, {n} reps, {dt * 1e3:.1f} ms each"}, dt
 
 
+_CPU_THREADS = None
+
+
+def _pick_cpu_threads(fn):
+    """The oracle is a chain of (1024 x 8192)-sized matmuls: on a 64-core host torch's default (every core) is slower
+    than a few threads (measured 0.039 vs 0.156 TFLOP/s).  Calibrate once: time one call at 4, 8, 16, ... threads and
+    keep the fastest, so that the CPU arm is the strongest baseline this host gives."""
+    global _CPU_THREADS
+    if _CPU_THREADS is None:
+        ncpu = os.cpu_count() or 1
+        cands = sorted({t for t in (4, 8, 16, 32, 64, ncpu) if t <= ncpu} | {min(ncpu, 4)})
+        best = (float("inf"), torch.get_num_threads())
+        for t in cands:
+            torch.set_num_threads(t)
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, (time.perf_counter() - t0, t))
+        _CPU_THREADS = best[1]
+    torch.set_num_threads(_CPU_THREADS)
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path (oracle port), timed per step."""
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; the CPU arm may use every host core
+    # torchrun pins OMP_NUM_THREADS=1; the CPU arm may use every host core - cpu_baseline() picks the fastest count
     mode = args.mode
     cb, _ = cpu_baseline(args.causal, mode, budget_s=2.0)  # warm
     vals = []
