@@ -321,7 +321,7 @@ def main():
 
     if rank == 0:
         cb = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only
             cb, _ = cpu_baseline(causal, mode)
         line = {
             "metric": metric_name(mode), "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
