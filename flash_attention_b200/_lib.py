@@ -14,6 +14,7 @@ from . import build as _build
 _LIB = None
 
 FP16, BF16, FP8_E4M3 = 0, 1, 2
+ENTRY_INFER, ENTRY_DENSE, ENTRY_VARLEN, ENTRY_KVCACHE = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp, _sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t
 
@@ -44,6 +45,7 @@ class FwdArgs(C.Structure):
         ("debug_s", _vp),
         ("p_dropout", C.c_float), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
         ("s_dmask", _vp),
+        ("entry", _i32),
     ]
 
 
@@ -128,8 +130,16 @@ def load():
     if _LIB is not None:
         return _LIB
     path = os.environ.get("FA_B200_LIB") or _build.LIB  # FA_B200_LIB: experiment variant built by build.build(out=...)
-    if path == _build.LIB and (not os.path.exists(path) or os.environ.get("FA_B200_REBUILD") == "1"):
-        _build.build(force=True)
+    if path == _build.LIB:
+        if not os.path.exists(path) or os.environ.get("FA_B200_REBUILD") == "1":
+            _build.build(force=True)
+        elif _build.needs_build():   # a source is newer than the .so: rebuild when a compiler is here, else say so
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001  (GPU boxes ship the prebuilt .so; mtimes of a fresh copy may be unordered)
+                import warnings
+
+                warnings.warn(f"libfa_b200.so is older than its sources and could not be rebuilt ({e}); loading it as is")
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing

@@ -13,17 +13,31 @@ NVCC_FLAGS = [
 ]
 
 
-def _newest_source_mtime():
-    m = 0.0
+STAMP = LIB + ".srchash"   # content hash of the sources the .so was built from (travels with it to the GPU box)
+
+
+def source_hash():
+    import hashlib
+
+    h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
+        for f in sorted(os.listdir(root)):
             if f.endswith((".cu", ".cuh", ".h")):
-                m = max(m, os.path.getmtime(os.path.join(root, f)))
-    return m
+                h.update(f.encode())
+                with open(os.path.join(root, f), "rb") as fh:
+                    h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
 
 
 def needs_build():
-    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest_source_mtime()
+    """Stale = built from different source CONTENT (mtimes do not survive the copy to a GPU box)."""
+    if not os.path.exists(LIB):
+        return True
+    try:
+        return open(STAMP).read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False, extra_flags=(), out=None):
@@ -44,6 +58,9 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
         print(log)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + log[-4000:])
+    if out == LIB and not extra_flags:
+        with open(STAMP, "w") as f:
+            f.write(source_hash() + "\n")
     return out
 
 

@@ -78,14 +78,15 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* ba
 }
 
 int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static std::atomic<int> sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;   // planner queries on a CPU-only host
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
   }
-  return sms;
+  return n;
 }
 
 static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
@@ -134,7 +135,8 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     return set_error("Number of heads in key/value must divide number of heads in query");
   if (a.softcap < 0.f) return set_error("softcap must be non-negative");
   if (mode == kVarlen && (!a.cu_seqlens_q || !a.cu_seqlens_k)) return set_error("cu_seqlens_q and cu_seqlens_k are required");
-  if ((a.cache_batch_idx || a.leftpad_k) && mode != kKvcache) return set_error("cache_batch_idx / leftpad_k are kvcache-only arguments");
+  if (a.cache_batch_idx && mode != kKvcache) return set_error("cache_batch_idx is a kvcache-only argument");
+  if (a.leftpad_k && mode == kDense) return set_error("leftpad_k is a varlen / kvcache argument");
   if (a.block_table && (a.cache_batch_idx || a.leftpad_k))
     return set_error("We don't support Paged KV and leftpad_k / cache_batch_idx running at the same time yet");
   if (a.block_table) {
@@ -235,13 +237,11 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
 template <typename T, int kD, int kTiles, bool kDropout = false>
 static int launch_fwd_kernel_t(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
   using Cfg = FwdCfg<kD, EltInfo<T>::kBytes, kTiles>;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = fa_fwd_kernel<T, kD, kTiles, kDropout>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(fwd): ") + cudaGetErrorString(e));
-    configured = true;
-  }
+  if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
+      e != cudaSuccess)
+    return set_error(std::string("cudaFuncSetAttribute(fwd): ") + cudaGetErrorString(e));
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
@@ -428,7 +428,14 @@ int fa_b200_mha_fwd_kvcache(const fa_b200_fwd_args* args, fa_b200_stream_t strea
   return run_fwd(*args, kKvcache, static_cast<cudaStream_t>(stream));
 }
 
-static FwdMode mode_of(const fa_b200_fwd_args* a) { return a->cu_seqlens_q ? kVarlen : (a->block_table || a->seqused_k ? kKvcache : kDense); }
+// which entry point the args are meant for: `entry` says so (the planner queries must agree with the launch: the kvcache
+// entry plans differently from the dense one even without cache_seqlens / block_table); 0 = infer from the pointers
+static FwdMode mode_of(const fa_b200_fwd_args* a) {
+  if (a->entry == FA_B200_ENTRY_DENSE) return kDense;
+  if (a->entry == FA_B200_ENTRY_VARLEN) return kVarlen;
+  if (a->entry == FA_B200_ENTRY_KVCACHE) return kKvcache;
+  return a->cu_seqlens_q ? kVarlen : (a->block_table || a->seqused_k ? kKvcache : kDense);
+}
 
 size_t fa_b200_fwd_workspace_bytes(const fa_b200_fwd_args* args) {
   FwdPlan pl;

@@ -16,7 +16,22 @@ int set_error(const std::string& msg);
 // rank-N tiled tensor map, 128-byte (default) or 64-byte swizzle, zero OOB fill; dims innermost first, strides in bytes (dims 1..rank-1)
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
-int num_sms();
+int num_sms();   // of the CURRENT device (cached per device)
+// One-time per-(kernel, device) setup: cudaFuncSetAttribute is per device / context, so a process that drives several GPUs
+// must raise the dynamic shared-memory limit on each of them (a per-process flag left the second device at the 48 KB default).
+struct PerDeviceOnce {
+  std::atomic<bool> done[64] = {};
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return f();
+    if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    cudaError_t e = f();
+    if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
+    return e;
+  }
+};
 // Block order.  Default is head-major (all blocks of one head are dispatched together: they share their streamed operands
 // through L2, which measured more important than a balanced tail: pure work-major order cost 10 % on causal problems).
 // The chunked work-major order keeps chunks of c adjacent blocks of a head together and dispatches heavy chunks of all

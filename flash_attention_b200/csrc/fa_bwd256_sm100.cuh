@@ -126,7 +126,7 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
         for (int it = 0; it < n_iter; ++it) {
           const int hq = hk * p.g + it / n_m;
           const int m = m_min + it % n_m;
-          const int64_t srow = (int64_t(bidb) * p.h + hq) * p.sq_r + m * 64;
+          const int64_t srow = ws_rows(p.cu_seqlens_q, bidb, p.h, hq, p.sq_r, p.ws_head_pitch).stat_base + m * 64;
           const int st = it & 1;
           mbar_wait(bar(B_QEO), (it & 1) ^ 1, 400);                  // S^T of tile it-1 done
           mbar_wait(bar(B_QEC0 + st), ((it >> 1) & 1) ^ 1, 401);     // dK of tile it-2 done
@@ -266,7 +266,7 @@ fa_bwd256_kernel(const __grid_constant__ BwdKernelParams p) {
         }
         named_bar_sync(1, 128);
       }
-      float* dst = p.dq_accum + ((int64_t(bidb) * p.h + hq) * p.sq_r + m * 64) * 256 + dcol;
+      float* dst = p.dq_accum + (ws_rows(p.cu_seqlens_q, bidb, p.h, hq, p.sq_r, p.ws_head_pitch).stat_base + m * 64) * 256 + dcol;
       const int rows = sq_b - m * 64;   // >= 1; rows beyond the sequence carry zeros and are skipped
 #pragma unroll
       for (int half = 0; half < 2; ++half) {

@@ -196,7 +196,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
           const int m = m_min + it % n_m;
           const int st = it & 1;
           const int qrow = q_off + m * 128;
-          const int64_t srow = (int64_t(bidb) * p.h + hq) * p.sq_r + m * 128;
+          const int64_t srow = ws_rows(p.cu_seqlens_q, bidb, p.h, hq, p.sq_r, p.ws_head_pitch).stat_base + m * 128;
           const uint32_t free_par = (it & 1) ^ 1;
           mbar_wait(bar(E_QB), free_par, 400);     // S^T of the previous iteration has read sQb
           if (rank == 0) mbar_arrive_expect_tx(bar(F_QB), 2 * 16384);
@@ -371,6 +371,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     const uint32_t t_dq = tS + 64 + (uint32_t(wq * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
     const uint32_t dqe = mapa_rank(bar(DQ_E), 0);
+    const WsRows ws = ws_rows(p.cu_seqlens_q, bidb, p.h, 0, p.sq_r, p.ws_head_pitch);   // tensor-map coordinates only
     for (int it = 0; it < n_iter; ++it) {
       const int hq = hk * p.g + it / n_m;
       const int m = m_min + it % n_m;
@@ -415,8 +416,8 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         fence_proxy_async();
         named_bar_sync(2, 128);
         if (leader) {
-          tma_reduce_add_4d(&p.tm_dq64, sDQ, c * 32, m * 128 + 64 * int(rank), hq, bidb);
-          tma_reduce_add_4d(&p.tm_dq64, sDQ + 8192, 64 + c * 32, m * 128 + 64 * int(rank), hq, bidb);
+          tma_reduce_add_4d(&p.tm_dq64, sDQ, c * 32, ws.tma_row0 + m * 128 + 64 * int(rank), hq, ws.tma_b);
+          tma_reduce_add_4d(&p.tm_dq64, sDQ + 8192, 64 + c * 32, ws.tma_row0 + m * 128 + 64 * int(rank), hq, ws.tma_b);
           tma_store_commit();
         }
       }

@@ -19,6 +19,7 @@ static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct BwdPlan {
   int kD, sq_r;
+  int64_t ws_rows_head;   // packed varlen layout: rows per head (0 = dense layout)
   int has_left, has_right, wl, wr;
   size_t off_lse, off_dps, off_dq, off_sem, total;
 };
@@ -50,12 +51,16 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   if (wr >= a.seqlen_k) wr = -1;
   if (a.is_causal) wr = 0;
   pl->has_left = wl >= 0; pl->has_right = wr >= 0; pl->wl = wl; pl->wr = wr;
-  const size_t stat = size_t(a.b) * a.h * pl->sq_r * sizeof(float);
+  // dense: (b, h, sq_r) rows; varlen: (h, R) rows with R = round4(total_q) + 132 * b + 128 (fa_bwd_sm100.cuh ws_rows):
+  // grows with total_q, not b * max_seqlen_q (reference: total_q + 128 * b, flash_api.cpp:1142-1159)
+  pl->ws_rows_head = varlen ? ((int64_t(a.total_q) + 3) / 4 * 4 + 132 * int64_t(a.b) + 128) : 0;
+  const size_t stat = (varlen ? size_t(a.h) * size_t(pl->ws_rows_head) : size_t(a.b) * a.h * pl->sq_r) * sizeof(float);
   pl->off_lse = 0;
   pl->off_dps = align256(stat);
   pl->off_dq = pl->off_dps + align256(stat);
   pl->off_sem = pl->off_dq + align256(stat * pl->kD);   // deterministic mode: one counter per (b, h, query block),
-  pl->total = pl->off_sem + align256(stat / 128 * (pl->kD == 256 ? 4 : 2));   // placed right behind dq_accum so one
+  const size_t sem = size_t(a.b) * a.h * (pl->sq_r / 128) * sizeof(int);   // semaphores stay (b, h, query block)
+  pl->total = pl->off_sem + align256(sem * (pl->kD == 256 ? 4 : 2));   // placed right behind dq_accum so one
                           // memset clears both (x2: the CTA-pair kernel orders each query half separately; x4: the
                           // head-dim 256 kernel has one chain per 64-query tile and output half)
   return 0;
@@ -64,13 +69,11 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
 template <typename T, int kD, bool kSoftcap, bool kDropout = false>
 static int launch_bwd_main(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
   using Cfg = BwdCfg<kD>;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = fa_bwd_kernel<T, kD, kSoftcap, kDropout>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(bwd): ") + cudaGetErrorString(e));
-    configured = true;
-  }
+  if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
+      e != cudaSuccess)
+    return set_error(std::string("cudaFuncSetAttribute(bwd): ") + cudaGetErrorString(e));
   if (kp.sched_lpt) grid = dim3(grid.y, grid.z, grid.x);   // (h_k, b, key blocks): key-block index slowest
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   g_launch_count++;
@@ -82,13 +85,11 @@ static int launch_bwd_main(const BwdKernelParams& kp, dim3 grid, cudaStream_t st
 // CTA-pair main loop (fa_bwd2_sm100.cuh): head dim 128 only
 template <typename T, bool kSoftcap, bool kDropout>
 static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = fa_bwd2_kernel<T, kSoftcap, kDropout>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(bwd2): ") + cudaGetErrorString(e));
-    configured = true;
-  }
+  if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Cfg::kSmemBytes); });
+      e != cudaSuccess)
+    return set_error(std::string("cudaFuncSetAttribute(bwd2): ") + cudaGetErrorString(e));
   grid.x = (grid.x + 1) / 2 * 2;  // whole pairs (compile-time cluster dims (2,1,1))
   if (kp.sched_lpt) {
     const unsigned pairs = grid.x / 2, c = unsigned(kp.sched_lpt);
@@ -104,13 +105,11 @@ static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t st
 // head dims 129..256 (fa_bwd256_sm100.cuh): two CTAs (output halves) per key block
 template <typename T, bool kSoftcap, bool kDropout>
 static int launch_bwd_hd256(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = fa_bwd256_kernel<T, kSoftcap, kDropout>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd256Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(bwd256): ") + cudaGetErrorString(e));
-    configured = true;
-  }
+  if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd256Cfg::kSmemBytes); });
+      e != cudaSuccess)
+    return set_error(std::string("cudaFuncSetAttribute(bwd256): ") + cudaGetErrorString(e));
   grid.x *= 2;
   kern<<<grid, Bwd256Cfg::kThreads, Bwd256Cfg::kSmemBytes, stream>>>(kp);
   g_launch_count++;
@@ -148,7 +147,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
     fa_bwd_preprocess<T><<<grid, 256, 0, stream>>>(
         reinterpret_cast<const T*>(a.out), reinterpret_cast<const T*>(a.dout), a.softmax_lse, dpsum, lse_log2, a.softmax_d,
         a.o_batch_stride, a.o_row_stride, a.o_head_stride, a.do_batch_stride, a.do_row_stride, a.do_head_stride,
-        a.cu_seqlens_q, a.b, a.h, a.seqlen_q, sq_r, a.d, a.total_q, clear_rows, kD);
+        a.cu_seqlens_q, a.b, a.h, a.seqlen_q, sq_r, a.d, a.total_q, clear_rows, kD, pl.ws_rows_head);
     g_launch_count++;
     if ((e = cudaGetLastError()) != cudaSuccess) return set_error(std::string("fa_bwd_preprocess launch: ") + cudaGetErrorString(e));
   }
@@ -170,8 +169,9 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   if (int rc = map16(&kp.tm_v, a.v, a.v_batch_stride, a.v_row_stride, a.v_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
   {
     constexpr uint64_t esz = 4;
-    uint64_t dims[4] = {uint64_t(kD), uint64_t(sq_r), uint64_t(a.h), uint64_t(a.b)};
-    uint64_t str[3] = {uint64_t(kD) * esz, uint64_t(sq_r) * kD * esz, uint64_t(a.h) * sq_r * kD * esz};
+    const uint64_t rows_head = varlen ? uint64_t(pl.ws_rows_head) : uint64_t(sq_r);
+    uint64_t dims[4] = {uint64_t(kD), rows_head, uint64_t(a.h), uint64_t(varlen ? 1 : a.b)};
+    uint64_t str[3] = {uint64_t(kD) * esz, rows_head * kD * esz, uint64_t(a.h) * rows_head * kD * esz};
     uint32_t box[4] = {uint32_t(128 / esz), 128, 1, 1};
     if (int rc = make_tmap(&kp.tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                            dq_accum, dims, str, box)) return rc;
@@ -191,8 +191,9 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
     if (int rc = map16(&kp.tm_dv, a.dv, a.dv_batch_stride, a.dv_row_stride, a.dv_head_stride, a.seqlen_k, a.total_k, a.h_k)) return rc;
     if (int rc = map64(&kp.tm_q64, a.q, a.q_batch_stride, a.q_row_stride, a.q_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
     if (int rc = map64(&kp.tm_do64, a.dout, a.do_batch_stride, a.do_row_stride, a.do_head_stride, a.seqlen_q, a.total_q, a.h)) return rc;
-    uint64_t dims[4] = {uint64_t(kD), uint64_t(sq_r), uint64_t(a.h), uint64_t(a.b)};
-    uint64_t str[3] = {uint64_t(kD) * 4, uint64_t(sq_r) * kD * 4, uint64_t(a.h) * sq_r * kD * 4};
+    const uint64_t rows_head = varlen ? uint64_t(pl.ws_rows_head) : uint64_t(sq_r);
+    uint64_t dims[4] = {uint64_t(kD), rows_head, uint64_t(a.h), uint64_t(varlen ? 1 : a.b)};
+    uint64_t str[3] = {uint64_t(kD) * 4, rows_head * kD * 4, uint64_t(a.h) * rows_head * kD * 4};
     uint32_t box[4] = {32, 64, 1, 1};
     if (int rc = make_tmap(&kp.tm_dq64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, dims, str, box)) return rc;
   }
@@ -206,6 +207,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   kp.alibi_slopes = a.alibi_slopes; kp.alibi_batch_stride = a.alibi_slopes_batch_stride;
   kp.b = a.b; kp.h = a.h; kp.h_k = a.h_k; kp.sq = a.seqlen_q; kp.sk = a.seqlen_k; kp.d = a.d; kp.g = a.h / a.h_k;
   kp.sq_r = sq_r;
+  kp.ws_head_pitch = pl.ws_rows_head;
   kp.dq_accum = dq_accum;
   kp.has_left = pl.has_left; kp.has_right = pl.has_right; kp.wl = pl.wl; kp.wr = pl.wr;
   kp.scale = a.softmax_scale;
@@ -246,7 +248,7 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
     dim3 cgrid((a.seqlen_q + 7) / 8, a.h, a.b);
     fa_bwd_convert_dq<T, kD><<<cgrid, 256, 0, stream>>>(dq_accum, reinterpret_cast<T*>(a.dq), a.dq_batch_stride, a.dq_row_stride,
                                                       a.dq_head_stride, a.cu_seqlens_q, a.h, a.seqlen_q, sq_r, a.d,
-                                                      a.softmax_scale);
+                                                      a.softmax_scale, pl.ws_rows_head);
     g_launch_count++;
     if ((e = cudaGetLastError()) != cudaSuccess) return set_error(std::string("fa_bwd_convert_dq launch: ") + cudaGetErrorString(e));
   }

@@ -50,7 +50,8 @@ struct BwdKernelParams {
   const float* alibi_slopes;
   int64_t alibi_batch_stride;
   int b, h, h_k, sq, sk, d, g;
-  int sq_r;                  // round128(max seqlen_q): row pitch of lse_log2 / dpsum / dq_accum
+  int sq_r;                  // round128(max seqlen_q): row pitch of lse_log2 / dpsum / dq_accum (dense layout)
+  int64_t ws_head_pitch;     // packed varlen layout: rows per head of lse_log2 / dpsum / dq_accum (see ws_rows below)
   int has_right, has_left, wl, wr;
   float scale;               // softmax_scale: dK is multiplied by it in the epilogue (dQ in the convert kernel)
   float scale_eff;           // scale of the logits inside exp: softcap if softcap > 0 else softmax_scale
@@ -61,6 +62,31 @@ struct BwdKernelParams {
   const uint64_t* rng_state;  // device copy of {seed, offset}; overrides drop.seed/off when non-null
   float* dq_accum;            // fa_bwd256_kernel only (adds its dQ partials with red.global instead of TMA): (b, h, sq_r, 256)
 };
+
+// Row addressing of the backward scratch (lse_log2, dpsum: one float per row; dq_accum: kD floats per row).
+//   dense  (b, h, sq_r)            row(b, h, r) = (b * H + h) * sq_r + r
+//   varlen (h, R)                  row(b, h, r) = h * R + (cu_seqlens_q[b] & ~3) + 132 * b + r
+// The packed form follows the reference's (total_q + 128 * batch) padding (flash_api.cpp:1142-1159) so that scratch
+// grows with total_q, not batch * max_seqlen_q; the start is rounded down to 4 rows (16-byte aligned bulk copies of
+// the statistics) and the per-batch pad is 132 so that a sequence's round128 rows never reach the next sequence's.
+struct WsRows {
+  int64_t stat_base;   // index of row 0 of (batch, head) in the statistics arrays / dq_accum rows
+  int tma_row0;        // row coordinate of row 0 in the dq_accum tensor map
+  int tma_b;           // batch coordinate in the dq_accum tensor map
+};
+__device__ __forceinline__ WsRows ws_rows(const int* cu_q, int bidb, int h, int head, int sq_r, int64_t head_pitch) {
+  WsRows w;
+  if (cu_q) {
+    w.tma_row0 = (cu_q[bidb] & ~3) + 132 * bidb;
+    w.tma_b = 0;
+    w.stat_base = int64_t(head) * head_pitch + w.tma_row0;
+  } else {
+    w.tma_row0 = 0;
+    w.tma_b = bidb;
+    w.stat_base = (int64_t(bidb) * h + head) * sq_r;
+  }
+  return w;
+}
 
 template <int kD>
 struct BwdCfg {
@@ -94,7 +120,7 @@ __global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o
                                                          int64_t o_bs, int64_t o_rs, int64_t o_hs, int64_t do_bs,
                                                          int64_t do_rs, int64_t do_hs, const int* __restrict__ cu_q,
                                                          int b, int h, int sq, int sq_r, int d, int total_q,
-                                                         float* __restrict__ dq_accum_rows, int kD) {
+                                                         float* __restrict__ dq_accum_rows, int kD, int64_t ws_head_pitch) {
   constexpr int kRows = 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + warp) * kRows;  // in [0, sq_r)
@@ -102,7 +128,9 @@ __global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o
   if (row0 >= sq_r) return;
   int q_off = 0, sq_b = sq;
   if (cu_q) { q_off = cu_q[bidb]; sq_b = cu_q[bidb + 1] - q_off; }
-  const int64_t sidx0 = (int64_t(bidb) * h + head) * sq_r + row0;
+  const int rows_b = cu_q ? (sq_b + 127) / 128 * 128 : sq_r;   // scratch rows of this (batch, head)
+  if (row0 >= rows_b) return;
+  const int64_t sidx0 = ws_rows(cu_q, bidb, h, head, sq_r, ws_head_pitch).stat_base + row0;
   const T* po = o + (cu_q ? 0 : bidb * o_bs) + int64_t(head) * o_hs;
   const T* pd = dout + (cu_q ? 0 : bidb * do_bs) + int64_t(head) * do_hs;
   float acc[kRows], l2[kRows];
@@ -129,7 +157,7 @@ __global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o
   if (dq_accum_rows) {
 #pragma unroll
     for (int r = 0; r < kRows; ++r)
-      if (row0 + r < sq_r && lane * 4 < kD)
+      if (row0 + r < rows_b && lane * 4 < kD)
         *reinterpret_cast<float4*>(dq_accum_rows + (sidx0 + r) * kD + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
@@ -142,7 +170,7 @@ __global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o
     float my_acc = 0.f;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) my_acc = lane == r ? acc[r] : my_acc;
-    if (row < sq_r) {
+    if (row < rows_b) {
       float my_l2 = INFINITY;
       if (row < sq_b) {
         const float l = cu_q ? lse[int64_t(head) * total_q + q_off + row] : lse[(int64_t(bidb) * h + head) * sq + row];
@@ -153,7 +181,7 @@ __global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o
       lse_log2[sidx] = my_l2;
       // API-visible softmax_d in the reference layouts: dense (b,h,sq_r) | varlen (h, total_q + 128*b)
       if (softmax_d) {
-        if (cu_q) { if (row < ((sq_b + 127) / 128) * 128) softmax_d[int64_t(head) * (total_q + 128 * b) + q_off + 128 * bidb + row] = my_acc; }
+        if (cu_q) softmax_d[int64_t(head) * (total_q + 128 * b) + q_off + 128 * bidb + row] = my_acc;
         else softmax_d[sidx] = my_acc;
       }
     }
@@ -165,7 +193,7 @@ template <typename T, int kD>
 __global__ void __launch_bounds__(256) fa_bwd_convert_dq(const float* __restrict__ dq_accum, T* __restrict__ dq,
                                                          int64_t dq_bs, int64_t dq_rs, int64_t dq_hs,
                                                          const int* __restrict__ cu_q, int h, int sq, int sq_r, int d,
-                                                         float scale) {
+                                                         float scale, int64_t ws_head_pitch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   const int head = blockIdx.y, bidb = blockIdx.z;
@@ -173,7 +201,7 @@ __global__ void __launch_bounds__(256) fa_bwd_convert_dq(const float* __restrict
   if (cu_q) { q_off = cu_q[bidb]; sq_b = cu_q[bidb + 1] - q_off; }
   if (row >= sq_b) return;
   T* dst = dq + (cu_q ? 0 : bidb * dq_bs) + int64_t(q_off + row) * dq_rs + int64_t(head) * dq_hs;
-  const float* src = dq_accum + ((int64_t(bidb) * h + head) * sq_r + row) * kD;
+  const float* src = dq_accum + (ws_rows(cu_q, bidb, h, head, sq_r, ws_head_pitch).stat_base + row) * kD;
   for (int c = lane * 4; c < d; c += 128) {
     const float4 v = *reinterpret_cast<const float4*>(src + c);
     uint2 o;
@@ -277,7 +305,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
           const int hq = hk * p.g + it / n_m;
           const int m = m_min + it % n_m;
           const int st = it & 1;
-          const int64_t srow = (int64_t(bidb) * p.h + hq) * p.sq_r + m * 128;
+          const int64_t srow = ws_rows(p.cu_seqlens_q, bidb, p.h, hq, p.sq_r, p.ws_head_pitch).stat_base + m * 128;
           mbar_wait(bar(B_QE0 + st), ((it >> 1) & 1) ^ 1, 400 + st);
           mbar_arrive_expect_tx(bar(B_QF0 + st), Cfg::kTileBytes + 1024);
 #pragma unroll
@@ -372,6 +400,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
     const int r = wq * 32 + lane;  // query row within the block
     const uint32_t t_dq = tDP + (uint32_t(wq * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
+    const WsRows ws = ws_rows(p.cu_seqlens_q, bidb, p.h, 0, p.sq_r, p.ws_head_pitch);   // tensor-map coordinates only
     int nbuf = 0;
     for (int it = 0; it < n_iter; ++it) {
       const int hq = hk * p.g + it / n_m;
@@ -423,7 +452,7 @@ fa_bwd_kernel(const __grid_constant__ BwdKernelParams p) {
           fence_proxy_async();
           named_bar_sync(2, 128);
           if (leader) {
-            tma_reduce_add_4d(&p.tm_dq, sDQ + buf * Cfg::kPanelBytes, half * 64 + c * 32, m * 128, hq, bidb);
+            tma_reduce_add_4d(&p.tm_dq, sDQ + buf * Cfg::kPanelBytes, half * 64 + c * 32, ws.tma_row0 + m * 128, hq, ws.tma_b);
             tma_store_commit();
           }
         }

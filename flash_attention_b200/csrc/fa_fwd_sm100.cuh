@@ -176,7 +176,11 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
   if (p.seqused_k) sk_b = p.seqused_k[bidb];
   if (p.seqused_q) sq_b = p.seqused_q[bidb];
-  if (p.leftpad_k) { k_off = p.leftpad_k[bidb]; sk_b -= k_off; }  // seqlen_k = seqused_k - leftpad_k (block_info.h:12-45)
+  if (p.leftpad_k) {  // keys start leftpad_k rows into the batch's rows; seqlen_k = seqused_k - leftpad_k (block_info.h:12-45)
+    const int lp = p.leftpad_k[bidb];
+    k_off += lp;
+    sk_b -= lp;
+  }
   const int rows_total = sq_b * p.gp;
   const int row0 = m_block * kRowsPerCta;
   if (row0 >= rows_total) return;  // uniform for the whole CTA, nothing allocated yet

@@ -254,7 +254,6 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_,
     _common_checks(q, k, v)
     if return_softmax:
         _check(p_dropout > 0.0, "return_softmax is only supported when p_dropout > 0.0")
-    _check(leftpad_k_ is None, "fa_b200: leftpad_k is not implemented")
     _check(cu_seqlens_q.dtype == torch.int32, "cu_seqlens_q must have dtype int32")
     _check(cu_seqlens_k.dtype == torch.int32, "cu_seqlens_k must have dtype int32")
     _check(cu_seqlens_q.is_cuda and cu_seqlens_k.is_cuda, "cu_seqlens must be on CUDA device")
@@ -323,6 +322,11 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k_,
     if seqused_q is not None:
         _check(seqused_q.dtype == torch.int32 and seqused_q.is_cuda and seqused_q.is_contiguous(), "seqused_q must be int32 contiguous cuda")
         a.seqused_q = _ptr(seqused_q)
+    if leftpad_k_ is not None:  # flash_api.cpp:740-747
+        _check(not paged, "We don't support Paged KV and leftpad_k running at the same time yet")
+        _check(leftpad_k_.dtype == torch.int32, "leftpad_k must have dtype int32")
+        _check(leftpad_k_.is_cuda and leftpad_k_.is_contiguous() and tuple(leftpad_k_.shape) == (b,), "leftpad_k must be (batch,) contiguous cuda")
+        a.leftpad_k = _ptr(leftpad_k_)
     a.softmax_scale, a.softcap = softmax_scale, softcap
     a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
     a.num_splits = 1
@@ -410,6 +414,7 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
     a.softmax_scale, a.softcap = softmax_scale, softcap
     a.is_causal, a.window_size_left, a.window_size_right = int(is_causal), window_size_left, window_size_right
     a.num_splits = num_splits
+    a.entry = _lib.ENTRY_KVCACHE   # the workspace query must plan like the kvcache launch does
     _alibi(a, alibi_slopes_, b, h)
     with torch.cuda.device(q.device):
         ws = _workspace(lib, a, q.device)  # noqa: F841

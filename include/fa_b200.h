@@ -45,6 +45,8 @@ enum fa_b200_dtype {
   FA_B200_FP8_E4M3 = 2 /* forward only; output is bf16 (spec: hopper/flash_api.cpp mha_fwd, flash_attn/cute/interface.py:637-643) */
 };
 
+enum fa_b200_entry { FA_B200_ENTRY_INFER = 0, FA_B200_ENTRY_DENSE = 1, FA_B200_ENTRY_VARLEN = 2, FA_B200_ENTRY_KVCACHE = 3 };
+
 /* Forward arguments (dense, varlen, paged-KV decode share one struct; unused pointers are NULL). */
 typedef struct fa_b200_fwd_args {
   /* tensors */
@@ -68,7 +70,8 @@ typedef struct fa_b200_fwd_args {
   const int32_t* seqused_k;    /* (b) or NULL: number of valid keys per batch (cache_seqlens) */
   const int32_t* seqused_q;    /* (b) or NULL: number of valid queries per batch (FA3 `seqused_q`); rows beyond are not written */
   const int32_t* cache_batch_idx; /* (b) or NULL: batch b reads cache row cache_batch_idx[b] (kvcache, not paged) */
-  const int32_t* leftpad_k;    /* (b) or NULL: keys of batch b start at row leftpad_k[b] (kvcache, not paged) */
+  const int32_t* leftpad_k;    /* (b) or NULL: keys of batch b start leftpad_k[b] rows into its rows and seqused_k counts from
+                                * the start of those rows (kvcache and varlen, not paged; block_info.h:12-45) */
   const int32_t* block_table;  /* (b, max_blocks_per_seq) or NULL */
   int64_t block_table_batch_stride;
   int32_t page_block_size;     /* multiple of 128 (reference requires 256: flash_api.cpp:1305) */
@@ -97,6 +100,11 @@ typedef struct fa_b200_fwd_args {
   /* return_softmax: optional (b, h, round128(seqlen_q), round128(seqlen_k)) buffer in q's dtype receiving the
    * normalised probabilities, negated where dropped ("for testing only", flash_attn_interface.py:1196) */
   void* s_dmask;
+  /* which entry point these args are for (enum fa_b200_entry).  The launch functions ignore it; the planner queries
+   * (fa_b200_fwd_workspace_bytes / _num_splits / _plan) use it so that their answer matches the launch -- the kvcache
+   * entry plans its splits differently from the dense one even when neither cache_seqlens nor block_table is given.
+   * 0 = infer from the pointers (cu_seqlens_q -> varlen, block_table | seqused_k -> kvcache, else dense). */
+  int32_t entry;
 } fa_b200_fwd_args;
 
 typedef struct fa_b200_bwd_args {

@@ -21,7 +21,8 @@ What is restated (reference file:line):
   * tanh soft-cap                         csrc/flash_attn/flash_api.cpp:130-134
   * LSE definition (natural log)          csrc/flash_attn/src/softmax.h:169-186
   * GQA head mapping h -> h // (H/H_k)    csrc/flash_attn/src/flash_fwd_kernel.h:155
-  * fp8 forward (descales, bf16 out)      flash_attn/cute/testing.py:326-470
+  * fp8 forward (descales, bf16 out, e4m3 `intermediate_dtype`)   flash_attn/cute/testing.py:326-470
+                                          (pinned by tests/golden/fp8_*.npz, oracle/make_golden.py)
   * split-KV combine                      csrc/flash_attn/src/flash_fwd_kernel.h:1117-1299
   * paged-KV gather                       csrc/flash_attn/src/flash_fwd_kernel.h:592-597
 """
@@ -125,6 +126,11 @@ def attention_oracle(
     lse_masked_value: float = float("inf"),
     dropout_p: float = 0.0,
     dropout_mask: Optional[torch.Tensor] = None,  # (b, h, sq, sk) bool, True = keep (tests/test_flash_attn.py:231,288-296)
+    p_quant: str = "unnormalized",  # what `p_dtype` rounds: "unnormalized" = exp(s - m) as the kernels do;
+                                    # "normalized" = softmax(s), the reference's `intermediate_dtype`
+                                    # (flash_attn/cute/testing.py:461-462)
+    reorder_ops: bool = False,      # scale K before the score GEMM and keep the scores in `compute_dtype`
+                                    # (the reference's low-precision baseline, flash_attn/cute/testing.py:381-386)
 ):
     """Returns (out (b,sq,h,dv) in q's dtype [bf16 if q is fp8], lse (b,h,sq) fp32).
 
@@ -140,16 +146,20 @@ def attention_oracle(
     if softmax_scale is None:
         softmax_scale = 1.0 / math.sqrt(d)
     qf, kf, vf = q.to(compute_dtype), k.to(compute_dtype), v.to(compute_dtype)
+    # de-scales are applied in fp32 and rounded back to the compute dtype (flash_attn/cute/testing.py:363-369)
     if q_descale is not None:
-        qf = qf * q_descale.to(compute_dtype).repeat_interleave(g, dim=1).view(b, 1, h, 1)
+        qf = (qf.float() * q_descale.float().repeat_interleave(g, dim=1).view(b, 1, h, 1)).to(compute_dtype)
     if k_descale is not None:
-        kf = kf * k_descale.to(compute_dtype).view(b, 1, hk, 1)
+        kf = (kf.float() * k_descale.float().view(b, 1, hk, 1)).to(compute_dtype)
     if v_descale is not None:
-        vf = vf * v_descale.to(compute_dtype).view(b, 1, hk, 1)
+        vf = (vf.float() * v_descale.float().view(b, 1, hk, 1)).to(compute_dtype)
     if g > 1:
         kf = kf.repeat_interleave(g, dim=2)
         vf = vf.repeat_interleave(g, dim=2)
-    s = torch.einsum("bihd,bjhd->bhij", qf, kf).float() * softmax_scale
+    if reorder_ops:
+        s = torch.einsum("bihd,bjhd->bhij", qf, kf * softmax_scale).float()
+    else:
+        s = torch.einsum("bihd,bjhd->bhij", qf, kf).float() * softmax_scale
     if softcap > 0:
         s = torch.tanh(s / softcap) * softcap
     if alibi_slopes is not None:
@@ -164,7 +174,10 @@ def attention_oracle(
     lse = (m_safe + torch.log(denom)).squeeze(-1)
     dead = denom.squeeze(-1) == 0
     lse = torch.where(dead, torch.full_like(lse, lse_masked_value), lse)
-    if p_dtype is not None:
+    if p_dtype is not None and p_quant == "normalized":
+        p = (e / denom.clamp_min(1e-30)).to(compute_dtype).to(p_dtype).to(compute_dtype)
+        o = torch.einsum("bhij,bjhd->bihd", p, vf)
+    elif p_dtype is not None:
         # the kernels quantise the un-normalised probabilities, then divide
         p = e.to(p_dtype).to(compute_dtype)
         o = torch.einsum("bhij,bjhd->bihd", p, vf) / denom.clamp_min(1e-30).permute(0, 2, 1, 3).to(compute_dtype)

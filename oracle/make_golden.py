@@ -89,5 +89,49 @@ def main():
         print("wrote", name, tuple(out.shape), float(out.float().abs().max()))
 
 
+FP8_REF = "/root/reference/flash_attn/cute/testing.py"
+FP8_CASES = [
+    # name, b, sq, sk, h, hk, d, causal, window(None = off), descales
+    ("fp8_noncausal_descale", 2, 96, 160, 4, 2, 128, False, (None, None), True),
+    ("fp8_causal", 1, 128, 128, 2, 2, 128, True, (None, None), False),
+    ("fp8_window_c4_mask", 1, 192, 192, 2, 1, 128, True, (48, 0), True),   # BASELINE C4's mask family (causal sliding window)
+    ("fp8_hd64_gqa", 1, 80, 112, 4, 1, 64, False, (None, None), True),
+]
+
+
+def main_fp8():
+    """FP8 e4m3 forward fixtures from the reference's FA4 oracle (flash_attn/cute/testing.py:326-470), loaded by file
+    path (pure torch, runs on CPU).  Stored per case, exactly as the reference's fp8 tests compute them
+    (tests/cute/test_flash_attn.py:413-448): `out_ref` = fp32 upcast, `out_pt` = bf16 math with reordered ops and the
+    softmax probabilities rounded to e4m3 (`intermediate_dtype`), plus the LSE of the upcast run."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_cute_testing", FP8_REF)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    f8 = torch.float8_e4m3fn
+    for name, b, sq, sk, h, hk, d, causal, window, descale in FP8_CASES:
+        torch.manual_seed(0)
+        # e4m3-representable inputs held in bf16 (the reference's dtype_ref for fp8), stored as raw e4m3 bytes
+        q8, k8, v8 = (torch.randn(b, s_, h_, d).to(f8) for s_, h_ in ((sq, h), (sk, hk), (sk, hk)))
+        q, k, v = (t.to(torch.bfloat16) for t in (q8, k8, v8))
+        ds = [(torch.rand(b, hk) + 0.5).float() if descale else None for _ in range(3)]
+        kw = dict(causal=causal, q_descale=ds[0], k_descale=ds[1], v_descale=ds[2], window_size=window)
+        out_ref, _, lse = ref.attention_ref(q, k, v, None, None, return_lse=True, **kw)
+        out_pt, _ = ref.attention_ref(q, k, v, None, None, upcast=False, reorder_ops=True, intermediate_dtype=f8, **kw)
+        np.savez_compressed(
+            os.path.join(OUT, name + ".npz"),
+            q=q8.view(torch.uint8).numpy(), k=k8.view(torch.uint8).numpy(), v=v8.view(torch.uint8).numpy(),
+            q_descale=(ds[0].numpy() if descale else np.zeros(0, np.float32)),
+            k_descale=(ds[1].numpy() if descale else np.zeros(0, np.float32)),
+            v_descale=(ds[2].numpy() if descale else np.zeros(0, np.float32)),
+            out_ref=out_ref.float().numpy(), out_pt=out_pt.float().numpy(), lse=lse.float().numpy(),
+            meta=np.array([b, sq, sk, h, hk, d, int(causal), -1 if window[0] is None else window[0],
+                           -1 if window[1] is None else window[1], int(descale)], np.int64),
+        )
+        print("wrote", name, tuple(out_ref.shape), float((out_pt.float() - out_ref.float()).abs().max()))
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    main()
+    main_fp8()

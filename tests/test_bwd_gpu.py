@@ -120,8 +120,10 @@ def test_gradient_linearity_full_size(fab):
 
 
 def test_full_size_slice_vs_oracle(fab):
-    """BASELINE headline shape (b4 h16 s8192 d128, causal): dK/dV of the last 256 keys only depend on the
-    last 256 queries (causal) -> compare that corner against the oracle on the slice."""
+    """BASELINE headline shape (b4 h16 s8192 d128, causal) against the CPU oracle on two corners: dQ of the first 256
+    queries (they only see the first 256 keys) and dK / dV of the LAST 256 keys (only the last 256 queries see them; their
+    softmax rows span all 8192 keys, bottom-right alignment makes the sliced problem the same geometry).  The whole
+    tensors are compared against the reference's FA2 kernels in tests/test_fa2_fullsize_gpu.py."""
     from oracle.attention_oracle import attention_oracle_bwd
 
     b, h, s, d = 4, 16, 8192, 128
@@ -133,6 +135,12 @@ def test_full_size_slice_vs_oracle(fab):
     sl = lambda t: t[bi:bi + 1, :n, hi:hi + 1].cpu()
     _, _, rdq, _, _ = attention_oracle_bwd(sl(q), sl(k), sl(v), sl(do), causal=True)
     assert (dq[bi:bi + 1, :n, hi:hi + 1].float().cpu() - rdq).abs().max().item() <= 3e-2 * max(1.0, rdq.abs().max().item())
+    hd = lambda t: t[bi:bi + 1, :, hi:hi + 1].cpu()
+    _, _, rdq2, rdk, rdv = attention_oracle_bwd(hd(q)[:, -n:], hd(k), hd(v), hd(do)[:, -n:], causal=True)
+    for name, got, ref in (("dq", dq[bi:bi + 1, -n:, hi:hi + 1], rdq2), ("dk", dk[bi:bi + 1, -n:, hi:hi + 1], rdk[:, -n:]),
+                           ("dv", dv[bi:bi + 1, -n:, hi:hi + 1], rdv[:, -n:])):
+        err = (got.float().cpu() - ref).abs().max().item()
+        assert err <= 3e-2 * max(1.0, ref.abs().max().item()), (name, err)
 
 
 @pytest.mark.parametrize("d", [128, 256])

@@ -132,3 +132,52 @@ def test_dropout_and_backward_argument_checks_without_gpu(fa_lib):
     assert fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw)) == 0 and b"dropout" in fa_lib.fa_b200_last_error()
     # pitched-copy helper rejects an unknown direction before touching CUDA
     assert fa_lib.fa_b200_memcpy2d_async(16, 64, 32, 64, 64, 1, 7, None) != 0 and b"kind" in fa_lib.fa_b200_last_error()
+
+
+def test_kvcache_plan_query_matches_the_launch_path(fa_lib):
+    """The workspace / plan queries must answer for the entry point that will be launched: the kvcache entry applies a
+    long-KV split refinement the dense one does not, so `flash_attn_with_kvcache(q, kc, vc)` WITHOUT cache_seqlens used
+    to be sized for 1 split and launched with 8 ('workspace too small for split-KV').  `entry` pins the mode."""
+    def args(entry, seqused):
+        a = _lib.FwdArgs()
+        a.dtype = _lib.BF16
+        a.q = a.k = a.v = a.out = a.softmax_lse = 16
+        a.b, a.seqlen_q, a.seqlen_k, a.h, a.h_k, a.d = 32, 1, 32768, 32, 8, 128
+        a.softmax_scale = 0.1
+        a.entry = entry
+        if seqused:
+            a.seqused_k = 16
+        return a
+
+    with_lens = args(_lib.ENTRY_INFER, True)
+    plain = args(_lib.ENTRY_KVCACHE, False)       # what fwd_kvcache passes when cache_seqlens is None
+    s1, s2 = fa_lib.fa_b200_fwd_num_splits(C.byref(with_lens)), fa_lib.fa_b200_fwd_num_splits(C.byref(plain))
+    assert s1 == s2 and s1 > 1
+    assert fa_lib.fa_b200_fwd_workspace_bytes(C.byref(with_lens)) == fa_lib.fa_b200_fwd_workspace_bytes(C.byref(plain)) > 0
+    # the launch path plans identically: with the queried workspace size the call gets past the workspace check and
+    # only fails later (no CUDA device / null workspace pointer are both fine for this host-only test)
+    plain.workspace_bytes = fa_lib.fa_b200_fwd_workspace_bytes(C.byref(plain))
+    plain.workspace = 256
+    rc = fa_lib.fa_b200_mha_fwd_kvcache(C.byref(plain), None)
+    assert not (rc != 0 and b"workspace too small" in fa_lib.fa_b200_last_error())
+    # the dense entry on the same shape does not take the refinement (documents why `entry` is needed)
+    dense = args(_lib.ENTRY_DENSE, False)
+    assert fa_lib.fa_b200_fwd_num_splits(C.byref(dense)) == 1
+
+
+def test_varlen_backward_workspace_grows_with_total_q_not_batch_times_max(fa_lib):
+    """a skewed packed batch (b = 512, one 8192-token sequence, the rest short) must not be sized
+    b * max_seqlen_q.  Layout: (h, round4(total_q) + 132 * b + 128) rows (reference: total_q + 128 * b, flash_api.cpp:1142-1159)."""
+    bw = _lib.BwdArgs()
+    bw.dtype = _lib.BF16
+    for f in ("dout", "q", "k", "v", "out", "softmax_lse", "dq", "dk", "dv", "cu_seqlens_q", "cu_seqlens_k"):
+        setattr(bw, f, 16)
+    b, h, d, max_s = 512, 32, 128, 8192
+    total = max_s + (b - 1) * 64
+    bw.b, bw.seqlen_q, bw.seqlen_k, bw.h, bw.h_k, bw.d = b, max_s, max_s, h, h, d
+    bw.total_q = bw.total_k = total
+    ws = fa_lib.fa_b200_bwd_workspace_bytes(C.byref(bw))
+    rows = (total + 3) // 4 * 4 + 132 * b + 128
+    assert ws > 0
+    assert ws <= h * rows * (d + 2) * 4 + (b * h * (max_s // 128) * 2 * 4) + 4096      # ~ 2 GB, was ~ 69 GB
+    assert ws < 0.05 * (b * h * max_s * d * 4)

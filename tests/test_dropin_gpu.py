@@ -13,7 +13,7 @@ import sys
 import pytest
 import torch
 
-from tests.util import check_fwd, make_qkv
+from tests.util import check_fwd, load_reference_fa2, make_qkv
 
 pytestmark = pytest.mark.gpu
 
@@ -24,10 +24,7 @@ def stack():
     if spec is None:
         pytest.skip("reference flash_attn package is not installed in this image")
     iface_path = os.path.join(list(spec.submodule_search_locations)[0], "flash_attn_interface.py")
-    try:
-        real = importlib.import_module("flash_attn_2_cuda")  # the reference's compiled kernels
-    except Exception as e:  # noqa: BLE001
-        pytest.skip(f"reference extension not importable: {e}")
+    real = load_reference_fa2()  # the reference's compiled kernels
     import flash_attention_b200 as fab
 
     sys.modules.pop("flash_attn_2_cuda", None)

@@ -148,3 +148,36 @@ def test_varlen_with_empty_sequences(fab):
     out.backward(torch.randn_like(out))
     assert torch.isfinite(q.grad).all() and torch.isfinite(k.grad).all() and torch.isfinite(v.grad).all()
     assert torch.all(q.grad[0:130] == 0) and torch.all(k.grad[0:77] == 0)  # no partner -> zero gradient
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_varlen_forward_leftpad_k(causal):
+    """mha_varlen_fwd's leftpad_k (flash_api.cpp:740-747, block_info.h:12-45): keys of batch b start leftpad_k[b] rows
+    into its packed rows and seqused_k counts from the start of those rows, i.e. batch b attends to rows
+    [cu_k[b] + leftpad[b], cu_k[b] + seqused_k[b])."""
+    from flash_attention_b200 import flash_attn_2_cuda as op
+    from oracle.attention_oracle import attention_oracle
+
+    h, hk, d = 4, 2, 128
+    lens_q, cap_k = [70, 128, 33], [300, 260, 129]          # packed rows reserved per batch
+    leftpad, used = [17, 0, 128], [250, 260, 129]           # seqused_k includes the left pad
+    cu_q = torch.tensor([0, 70, 198, 231], dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor([0, 300, 560, 689], dtype=torch.int32, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(231, h, d, device="cuda", dtype=torch.bfloat16, generator=g)
+    k = torch.randn(689, hk, d, device="cuda", dtype=torch.bfloat16, generator=g)
+    v = torch.randn(689, hk, d, device="cuda", dtype=torch.bfloat16, generator=g)
+    lp = torch.tensor(leftpad, dtype=torch.int32, device="cuda")
+    su = torch.tensor(used, dtype=torch.int32, device="cuda")
+    out, lse, _, _ = op.varlen_fwd(q, k, v, None, cu_q, cu_k, su, lp, None, None, max(lens_q), max(cap_k), 0.0, d ** -0.5,
+                                   False, causal, -1, -1, 0.0, False, None)
+    for b in range(3):
+        qs = q[int(cu_q[b]):int(cu_q[b + 1])].unsqueeze(0).cpu()
+        lo, hi = int(cu_k[b]) + leftpad[b], int(cu_k[b]) + used[b]
+        ref, lse_ref = attention_oracle(qs, k[lo:hi].unsqueeze(0).cpu(), v[lo:hi].unsqueeze(0).cpu(), causal=causal)
+        got = out[int(cu_q[b]):int(cu_q[b + 1])].float().cpu()
+        assert (got - ref[0].float()).abs().max().item() <= 2e-2, b
+        got_lse = lse[:, int(cu_q[b]):int(cu_q[b + 1])].cpu()
+        fin = torch.isfinite(lse_ref[0])
+        assert torch.equal(torch.isfinite(got_lse), fin)
+        assert (got_lse[fin] - lse_ref[0][fin]).abs().max().item() <= 2e-3 * 8

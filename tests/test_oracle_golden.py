@@ -9,7 +9,9 @@ import torch
 
 from oracle.attention_oracle import attention_oracle, attention_oracle_bwd, visible_mask
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = [p for p in _ALL if not os.path.basename(p).startswith("fp8_")]
+GOLD_FP8 = [p for p in _ALL if os.path.basename(p).startswith("fp8_")]
 
 
 def _load(path):
@@ -39,6 +41,41 @@ def test_oracle_matches_reference_golden(path):
     rs = torch.from_numpy(z["attn_rowsum"])
     dead_ref = rs < 0.5
     assert torch.equal(dead_ref, torch.isinf(lse) & (lse > 0))
+
+
+def load_fp8_golden(path):
+    """(meta, q8, k8, v8, descales, out_ref, out_pt, lse) of one fp8 fixture (oracle/make_golden.py:main_fp8)."""
+    z = np.load(path)
+    b, sq, sk, h, hk, d, causal, wl, wr, descale = [int(x) for x in z["meta"]]
+    f8 = torch.float8_e4m3fn
+    q8, k8, v8 = (torch.from_numpy(z[n]).view(f8) for n in ("q", "k", "v"))
+    ds = [torch.from_numpy(z[n]) if descale else None for n in ("q_descale", "k_descale", "v_descale")]
+    m = dict(b=b, sq=sq, sk=sk, h=h, hk=hk, d=d, causal=bool(causal), window=(wl, wr))
+    return m, q8, k8, v8, ds, torch.from_numpy(z["out_ref"]), torch.from_numpy(z["out_pt"]), torch.from_numpy(z["lse"])
+
+
+@pytest.mark.parametrize("path", GOLD_FP8, ids=[os.path.basename(p)[:-4] for p in GOLD_FP8])
+def test_fp8_oracle_matches_reference_golden(path):
+    """The fp8 branch of the oracle is pinned to the reference's FA4 oracle (flash_attn/cute/testing.py:326-470):
+    fp32-upcast output + LSE, and the low-precision baseline with e4m3-rounded probabilities (`intermediate_dtype`)."""
+    m, q8, k8, v8, ds, out_ref, out_pt, lse_ref = load_fp8_golden(path)
+    kw = dict(causal=m["causal"], window=m["window"], q_descale=ds[0], k_descale=ds[1], v_descale=ds[2])
+    bf = torch.bfloat16
+    out, lse = attention_oracle(q8.to(bf).float(), k8.to(bf).float(), v8.to(bf).float(), **kw)
+    # the reference returns both in the inputs' dtype (bf16): equal after the same rounding, up to one bf16 ulp where
+    # fp32 op-order noise straddles a rounding boundary
+    ulp = 2.0 ** -8
+    assert (out.to(bf).float() - out_ref).abs().max().item() <= ulp * max(1.0, out_ref.abs().max().item())
+    assert (out.to(bf).float() != out_ref).float().mean().item() < 0.01
+    assert (lse.to(bf).float() - lse_ref).abs().max().item() <= ulp * max(1.0, lse_ref.abs().max().item())
+    # low-precision baseline: bf16 math, K scaled before the GEMM, softmax(S) rounded to e4m3
+    pt, _ = attention_oracle(q8.to(bf), k8.to(bf), v8.to(bf), compute_dtype=bf, reorder_ops=True,
+                             p_dtype=torch.float8_e4m3fn, p_quant="normalized", **kw)
+    err_pt = (pt.float() - out_pt).abs().max().item()
+    base = (out_pt - out_ref).abs().max().item()   # what the rounding itself costs (the tolerance yardstick)
+    assert err_pt <= 0.5 * base + 1e-3, (err_pt, base)
+    # and the yardstick itself agrees: |pt - ref| of the restatement within 25 % of the reference's
+    assert abs((pt.float() - out).abs().max().item() - base) <= 0.25 * base + 1e-3
 
 
 def test_mask_bottom_right_alignment():

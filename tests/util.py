@@ -59,3 +59,33 @@ def bwd_tolerances(q, k, v, dout, **kw):
         atol = 2 * (g32 + 0.3 - 0.3 - g32).abs().max().item()
         res[n] = (g32, 3 * (gl.float() - g32).abs().max().item() + atol)
     return res
+
+
+_REAL_FA2 = None
+
+
+def load_reference_fa2():
+    """The reference's own compiled FA2 kernels: the `flash_attn_2_cuda` extension of the flash_attn wheel installed in the
+    image (sm80 mma.sync code built for sm_100).  Imported once per process under its real name even if
+    `flash_attention_b200.install()` has since put this library's operator module into sys.modules under that name."""
+    global _REAL_FA2
+    if _REAL_FA2 is None:
+        import importlib
+        import sys
+
+        import pytest
+
+        ours = sys.modules.pop("flash_attn_2_cuda", None)
+        try:
+            mod = importlib.import_module("flash_attn_2_cuda")
+        except Exception as e:  # noqa: BLE001
+            pytest.skip(f"reference FA2 extension not importable: {e}")
+        finally:
+            if ours is not None:
+                sys.modules["flash_attn_2_cuda"] = ours
+            else:
+                sys.modules.pop("flash_attn_2_cuda", None)
+        if not getattr(mod, "__file__", "").endswith(".so"):
+            pytest.skip("flash_attn_2_cuda resolves to a non-compiled module")
+        _REAL_FA2 = mod
+    return _REAL_FA2
