@@ -12,12 +12,30 @@ __version__ = "0.1.0"
 
 
 def install(name: str = "flash_attn_2_cuda"):
-    """Register this package's operator module as `flash_attn_2_cuda` (the extension module the
+    """Register this package's COMPILED operator module as `flash_attn_2_cuda` (the extension module the
     reference's flash_attn_interface.py imports, flash_attn/flash_attn_interface.py:23)."""
-    from . import flash_attn_2_cuda as mod
+    from . import flash_attn_2_cuda as loader
 
-    sys.modules[name] = mod
-    return mod
+    sys.modules[name] = loader.compiled_module
+    return loader.compiled_module
+
+
+def install_fa3():
+    """Make `import flash_attn_3._C` (hopper/flash_attn_interface.py:24) resolve to this package's compiled module, whose
+    import registers TORCH_LIBRARY(flash_attn_3) {fwd, bwd, fwd_combine, get_scheduler_metadata} (csrc/ext/flash_attn_3_ops.cpp),
+    so that the reference's FA3 interface file runs unchanged on these kernels via `torch.ops.flash_attn_3`."""
+    import types
+
+    from . import flash_attn_2_cuda as loader
+
+    pkg = sys.modules.get("flash_attn_3")
+    if pkg is None:
+        pkg = types.ModuleType("flash_attn_3")
+        pkg.__path__ = []
+        sys.modules["flash_attn_3"] = pkg
+    pkg._C = loader.compiled_module
+    sys.modules["flash_attn_3._C"] = loader.compiled_module
+    return loader.compiled_module
 
 
 def __getattr__(attr):

@@ -45,7 +45,7 @@ class FwdArgs(C.Structure):
         ("debug_s", _vp),
         ("p_dropout", C.c_float), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
         ("s_dmask", _vp),
-        ("entry", _i32),
+        ("entry", _i32), ("sm_margin", _i32),
     ]
 
 
@@ -73,7 +73,7 @@ class BwdArgs(C.Structure):
         ("deterministic", _i32),
         ("workspace", _vp), ("workspace_bytes", _sz),
         ("p_dropout", C.c_float), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
-        ("rng_state", _vp),
+        ("rng_state", _vp), ("sm_margin", _i32),
     ]
 
 
@@ -111,6 +111,7 @@ SYMBOLS = {
     "fa_b200_kvcache_append": (C.c_int, [C.POINTER(AppendArgs), _vp]),
     "fa_b200_sizeof_append_args": (_sz, []),
     "fa_b200_memcpy2d_async": (C.c_int, [_vp, _sz, _vp, _sz, _sz, _sz, _i32, _vp]),
+    "fa_b200_write_rng_state": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "fa_b200_num_splits_heuristic": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fa_b200_last_error": (C.c_char_p, []),
     "fa_b200_sizeof_fwd_args": (_sz, []),
@@ -140,7 +141,7 @@ def load():
                 import warnings
 
                 warnings.warn(f"libfa_b200.so is older than its sources and could not be rebuilt ({e}); loading it as is")
-    lib = C.CDLL(path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)   # global: the compiled operator module (ext/) resolves its libfa_b200.so dependency to THIS object
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res

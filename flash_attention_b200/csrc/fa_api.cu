@@ -46,8 +46,45 @@ static EncodeTiledFn get_encode_fn() {
 
 // rank-N tiled tensor map, 128-byte swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES
 // for dims 1..rank-1.
+//
+// Descriptors are cached per thread, keyed on everything that defines them (base pointer, dtype, rank, dims, strides, box,
+// swizzle): a training loop calls with the same allocator-recycled buffers step after step, and a forward + backward
+// pair encodes 3 + 10 maps -- the driver call costs more than the rest of the host path (tools/probe_overhead.py).
+struct TmapKey {
+  const void* base;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  int32_t dt, rank, swizzle, pad;
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+static inline uint64_t tmap_hash(const TmapKey& k) {
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+  return h;
+}
+static bool tmap_cache_enabled() {
+  static int on = [] { const char* e = getenv("FA_B200_TMAP_CACHE"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  constexpr int kSlots = 256;
+  thread_local TmapSlot cache[kSlots];
+  TmapKey key;
+  memset(&key, 0, sizeof key);
+  key.base = base; key.dt = int32_t(dt); key.rank = rank; key.swizzle = swizzle_bytes;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; if (i > 0) key.strides[i - 1] = strides_bytes[i - 1]; }
+  TmapSlot& slot = cache[tmap_hash(key) % kSlots];
+  if (tmap_cache_enabled() && slot.valid && memcmp(&slot.key, &key, sizeof key) == 0) {
+    *out = slot.map;
+    return 0;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   cuuint64_t gdim[5], gstr[4];
@@ -74,6 +111,9 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* ba
              bdim[1], bdim[2], rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0);
     return set_error(buf);
   }
+  slot.key = key;
+  slot.map = *out;
+  slot.valid = true;
   return 0;
 }
 
@@ -134,7 +174,10 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   if (a.h <= 0 || a.h_k <= 0 || a.h % a.h_k != 0)
     return set_error("Number of heads in key/value must divide number of heads in query");
   if (a.softcap < 0.f) return set_error("softcap must be non-negative");
-  if (mode == kVarlen && (!a.cu_seqlens_q || !a.cu_seqlens_k)) return set_error("cu_seqlens_q and cu_seqlens_k are required");
+  // packed queries; keys are packed too (cu_seqlens_k) or batched / paged with per-batch lengths (FA3: hopper/flash_api.cpp:742-760)
+  if (mode == kVarlen && !a.cu_seqlens_q) return set_error("cu_seqlens_q is required");
+  if (mode == kVarlen && !a.cu_seqlens_k && !a.block_table && !a.seqused_k)
+    return set_error("cu_seqlens_k (packed keys) or seqused_k / block_table (batched or paged keys) is required");
   if (a.cache_batch_idx && mode != kKvcache) return set_error("cache_batch_idx is a kvcache-only argument");
   if (a.leftpad_k && mode == kDense) return set_error("leftpad_k is a varlen / kvcache argument");
   if (a.block_table && (a.cache_batch_idx || a.leftpad_k))
@@ -532,6 +575,15 @@ int fa_b200_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t 
   cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height,
                                     kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return set_error(std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(e));
+  return 0;
+}
+__global__ void fa_write_rng_state_kernel(uint64_t* dst, uint64_t seed, uint64_t offset) { dst[0] = seed; dst[1] = offset; }
+int fa_b200_write_rng_state(uint64_t* dst, uint64_t seed, uint64_t offset, fa_b200_stream_t stream) {
+  if (!dst) return set_error("null pointer");
+  fa_write_rng_state_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(dst, seed, offset);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_write_rng_state_kernel launch: ") + cudaGetErrorString(e));
   return 0;
 }
 const char* fa_b200_last_error(void) { return g_last_error.c_str(); }

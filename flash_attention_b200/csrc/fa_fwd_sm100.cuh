@@ -139,6 +139,15 @@ __device__ unsigned long long g_fwd_ts[16 * 16];   // [iteration - 8][event]
 #ifndef FA_FWD_POLY_DEG_FP8
 #define FA_FWD_POLY_DEG_FP8 3
 #endif
+#ifndef FA_FWD_EXP_PIPE
+#define FA_FWD_EXP_PIPE 1   // 1: software-pipelined exponential phase (see the softmax loop); 0: the round-1 loop
+#endif
+#ifndef FA_FWD_POLY8
+#define FA_FWD_POLY8 (2 * FA_FWD_POLY_PAIRS)   // pipelined loop: polynomial pairs out of every 8 pairs (16 scores)
+#endif
+#ifndef FA_FWD_POLY8_FP8
+#define FA_FWD_POLY8_FP8 (2 * FA_FWD_POLY_PAIRS_FP8)
+#endif
 #ifndef FA_FWD_POLY_PAIRS
 #define FA_FWD_POLY_PAIRS 1  // measured on B200 (r01): 0 -> 1315, 1 -> 1339, 2 -> 1307, 3 -> 1147, 4 -> 1046 TFLOP/s fwd
 #endif
@@ -554,6 +563,66 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         // of MUFU.EX2 (the MUFU unit, 16 op/clk/SM, is otherwise as busy as the tensor pipe).
         const uint64_t sc2 = pack2(scale_log2, scale_log2), ng2 = pack2(neg_ms, neg_ms);
         uint64_t acc_a = pack2(0.f, 0.f), acc_b = pack2(0.f, 0.f);
+#if FA_FWD_EXP_PIPE
+        if constexpr (!kDropout) {
+        // Software-pipelined in chunks of 16 scores: stage A(k) scales the chunk (FMA pipe), stage B(k) takes the
+        // exponentials (MUFU, and the polynomial share on the FMA pipe), adds the row sum and packs.  ptxas schedules the
+        // fully unrolled block greedily and used to issue every scaling FFMA2 first (they are all ready when the row has
+        // been loaded), which left a MUFU-bound tail of ~75 back-to-back MUFU.EX2 with an idle FMA pipe: the phases ran in
+        // sequence, not in parallel (profiles/r01_sass_*; 1.66k clk for 128 exponentials vs ~0.8k of either pipe).  The
+        // scale factor of chunk k+1 is therefore made to DEPEND on an exponential of chunk k-1 (one extra FFMA2 with a zero
+        // multiplicand, which the assembler cannot fold): A(k+1) can only issue while B(k) is in flight, so both pipes stay busy.
+        const uint64_t zero2 = pack2(0.f, 0.f);
+        uint32_t pk[16];
+        uint64_t tok_prev = zero2, tok_cur = zero2;   // an exponential pair of chunk k-1 / k
+        auto stage_a = [&](int k, uint64_t sc) {
+#pragma unroll
+          for (int c = 0; c < 16; c += 2)
+            unpack2(fma2(pack2(s[16 * k + c], s[16 * k + c + 1]), sc, ng2), s[16 * k + c], s[16 * k + c + 1]);
+        };
+        stage_a(0, sc2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k + 1 < 8) stage_a(k + 1, k == 0 ? sc2 : fma2(tok_prev, zero2, sc2));
+          float ee[4];
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const int col = 16 * k + c;
+            float e0, e1;
+            if ((c >> 1) < 8 - (kFp8 ? FA_FWD_POLY8_FP8 : FA_FWD_POLY8)) {
+              e0 = ex2(s[col]);
+              e1 = ex2(s[col + 1]);
+            } else {
+              ex2_poly2_nz(pack2(s[col], s[col + 1]), e0, e1);
+            }
+            const uint64_t e2 = pack2(e0, e1);
+            if (c & 2) acc_b = add2(acc_b, e2);
+            else acc_a = add2(acc_a, e2);
+            if (c == 10) { tok_prev = tok_cur; tok_cur = e2; }
+            if constexpr (kFp8) {
+              ee[c & 2] = e0;
+              ee[(c & 2) + 1] = e1;
+              if (c & 2) pk[(col & 31) / 4] = pack_e4m3x4(ee[0], ee[1], ee[2], ee[3]);
+            } else {
+              pk[(col & 31) / 2] = Elt<T>::pack(e0, e1);
+            }
+          }
+          if (k & 1) {   // 32 columns done
+            const int cc = 32 * (k >> 1);
+            if constexpr (kFp8) tmem_st_x8(tS + cc / 4, pk);
+            else tmem_st_x16(tS + cc / 2, pk);
+            if (cc == 32 || cc == 96) {  // half of P is in TMEM: let the first / second half of P V start
+              tmem_wait_st();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_p_full(tile) + (cc == 96 ? 16u : 0u));
+              if (wq == 0 && lane == 0) FTS((cc == 96 ? 11 : 10) + 4 * tile);
+            }
+          }
+        }
+        } else
+#endif
+        {
 #pragma unroll
         for (int cc = 0; cc < 128; cc += 32) {
           uint32_t pk[16];
@@ -599,6 +668,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
             if (wq == 0 && lane == 0) FTS((cc == 96 ? 11 : 10) + 4 * tile);
           }
         }
+        }
         {
           float a0, a1, b0, b1;
           unpack2(acc_a, a0, a1);
@@ -609,7 +679,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
 
       // ---------------------------------------------------------------- epilogue
       float inv = 0.f, lse_val;
-      const bool dead = !(row_sum > 0.f);  // also catches NaN
+      // no visible key at all: the reference max never left -inf (the polynomial exp2 of the pipelined loop returns
+      // 2^-125 * p, not 0, for a masked score, so the row sum alone does not tell); !(row_sum > 0) also catches NaN
+      const bool dead = m_ref == kNegInf || !(row_sum > 0.f);
       if (!dead) {
         inv = descale_v / row_sum;
         if constexpr (kDropout) inv *= p.drop.rp;  // dropout.h:apply_dropout rescale, folded into the normalisation

@@ -357,6 +357,27 @@ __device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& 
   r1 = z1 ? 0.f : __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
+// Same polynomial without the exact-zero select: inputs are clamped at -125, so a masked (-inf) score yields 2^-125 * p
+// (~2e-38) instead of 0.  Harmless wherever the row is normalised by a finite row sum; callers that need "fully masked
+// row" detection test the row max instead of `row_sum == 0` (saves one FSETP + select per element).
+__device__ __forceinline__ void ex2_poly2_nz(uint64_t x, float& r0, float& r1) {
+  const float kMagic = 12582912.0f;
+  float x0, x1;
+  unpack2(x, x0, x1);
+  x = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t t = add2(x, pack2(kMagic, kMagic));
+  const uint64_t n = add2(t, pack2(-kMagic, -kMagic));
+  const uint64_t f = fma2(n, pack2(-1.0f, -1.0f), x);
+  uint64_t pl = fma2(f, pack2(0.0551716648f, 0.0551716648f), pack2(0.2426111251f, 0.2426111251f));
+  pl = fma2(pl, f, pack2(0.6932609677f, 0.6932609677f));
+  pl = fma2(pl, f, pack2(0.9999280572f, 0.9999280572f));
+  float t0, t1, p0, p1;
+  unpack2(t, t0, t1);
+  unpack2(pl, p0, p1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // degree-2 variant (rel. err 1.7e-3): enough when the result is quantised to e4m3 (3 mantissa bits); one FFMA2 less
 __device__ __forceinline__ void ex2_poly2_deg2(float x0, float x1, float& r0, float& r1) {
   const float kMagic = 12582912.0f;

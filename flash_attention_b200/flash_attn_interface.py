@@ -10,6 +10,13 @@ from typing import Optional, Tuple
 import torch
 
 from . import flash_attn_2_cuda as _op
+from . import ops as _ops  # noqa: F401  registers the fa_b200::{fwd,varlen_fwd,bwd,varlen_bwd} custom ops + fakes
+
+
+def _tracing() -> bool:
+    """True while torch.compile / export captures a graph: route through the registered custom ops (opaque to the tracer,
+    shapes from their fakes); eager calls go straight to the compiled module."""
+    return torch.compiler.is_compiling()
 
 
 def _c(x):
@@ -28,9 +35,14 @@ class _FlashAttnFunc(torch.autograd.Function):
             softmax_scale = q.shape[-1] ** (-0.5)
         d = q.shape[-1]
         qp, kp, vp = (_c(_pad8(t, d)) for t in (q, k, v))
-        out_p, lse, S_dmask, rng_state = _op.fwd(qp, kp, vp, None, alibi_slopes, dropout_p, softmax_scale, causal,
-                                                 window_size[0], window_size[1], softcap,
-                                                 return_softmax and dropout_p > 0, None)
+        if _tracing():
+            out_p, lse, S_dmask, rng_state = torch.ops.fa_b200.fwd(qp, kp, vp, dropout_p, softmax_scale, causal, window_size[0],
+                                                                   window_size[1], softcap, alibi_slopes,
+                                                                   return_softmax and dropout_p > 0)
+        else:
+            out_p, lse, S_dmask, rng_state = _op.fwd(qp, kp, vp, None, alibi_slopes, dropout_p, softmax_scale, causal,
+                                                     window_size[0], window_size[1], softcap,
+                                                     return_softmax and dropout_p > 0, None)
         ctx.save_for_backward(qp, kp, vp, out_p, lse, rng_state)
         ctx.args = (dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d)
         out = out_p[..., :d]
@@ -42,8 +54,12 @@ class _FlashAttnFunc(torch.autograd.Function):
         dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d = ctx.args
         dq, dk, dv = torch.empty_like(qp), torch.empty_like(kp), torch.empty_like(vp)
         dout_p = _c(_pad8(dout, d))
-        _op.bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, alibi_slopes, dropout_p, softmax_scale, causal,
-                window_size[0], window_size[1], softcap, deterministic, None, rng_state)
+        if _tracing():
+            torch.ops.fa_b200.bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, dropout_p, softmax_scale, causal, window_size[0],
+                                  window_size[1], softcap, alibi_slopes, deterministic, rng_state)
+        else:
+            _op.bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, alibi_slopes, dropout_p, softmax_scale, causal,
+                    window_size[0], window_size[1], softcap, deterministic, None, rng_state)
         return dq[..., :d], dk[..., :d], dv[..., :d], None, None, None, None, None, None, None, None
 
 
@@ -55,10 +71,15 @@ class _FlashAttnVarlenFunc(torch.autograd.Function):
             softmax_scale = q.shape[-1] ** (-0.5)
         d = q.shape[-1]
         qp, kp, vp = (_c(_pad8(t, d)) for t in (q, k, v))
-        out_p, lse, S_dmask, rng_state = _op.varlen_fwd(qp, kp, vp, None, cu_q, cu_k, None, None, block_table,
-                                                        alibi_slopes, max_q, max_k, dropout_p, softmax_scale, False,
-                                                        causal, window_size[0], window_size[1], softcap,
-                                                        return_softmax and dropout_p > 0, None)
+        if _tracing():
+            out_p, lse, S_dmask, rng_state = torch.ops.fa_b200.varlen_fwd(
+                qp, kp, vp, cu_q, cu_k, max_q, max_k, dropout_p, softmax_scale, causal, window_size[0], window_size[1], softcap,
+                alibi_slopes, return_softmax and dropout_p > 0, block_table, None, None, False)
+        else:
+            out_p, lse, S_dmask, rng_state = _op.varlen_fwd(qp, kp, vp, None, cu_q, cu_k, None, None, block_table,
+                                                            alibi_slopes, max_q, max_k, dropout_p, softmax_scale, False,
+                                                            causal, window_size[0], window_size[1], softcap,
+                                                            return_softmax and dropout_p > 0, None)
         ctx.save_for_backward(qp, kp, vp, out_p, lse, cu_q, cu_k, rng_state)
         ctx.args = (max_q, max_k, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d)
         out = out_p[..., :d]
@@ -70,9 +91,14 @@ class _FlashAttnVarlenFunc(torch.autograd.Function):
         max_q, max_k, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic, d = ctx.args
         dq, dk, dv = torch.empty_like(qp), torch.empty_like(kp), torch.empty_like(vp)
         dout_p = _c(_pad8(dout, d))
-        _op.varlen_bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, cu_q, cu_k, alibi_slopes, max_q, max_k, dropout_p,
-                       softmax_scale, False, causal, window_size[0], window_size[1], softcap, deterministic, None,
-                       rng_state)
+        if _tracing():
+            torch.ops.fa_b200.varlen_bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, cu_q, cu_k, max_q, max_k, dropout_p,
+                                         softmax_scale, causal, window_size[0], window_size[1], softcap, alibi_slopes,
+                                         deterministic, rng_state, False)
+        else:
+            _op.varlen_bwd(dout_p, qp, kp, vp, out_p, lse, dq, dk, dv, cu_q, cu_k, alibi_slopes, max_q, max_k, dropout_p,
+                           softmax_scale, False, causal, window_size[0], window_size[1], softcap, deterministic, None,
+                           rng_state)
         return (dq[..., :d], dk[..., :d], dv[..., :d]) + (None,) * 13
 
 

@@ -105,6 +105,8 @@ typedef struct fa_b200_fwd_args {
    * entry plans its splits differently from the dense one even when neither cache_seqlens nor block_table is given.
    * 0 = infer from the pointers (cu_seqlens_q -> varlen, block_table | seqused_k -> kvcache, else dense). */
   int32_t entry;
+  /* FA3 `sm_margin`: leave this many SMs free (persistent grids are sized num_SMs - sm_margin) */
+  int32_t sm_margin;
 } fa_b200_fwd_args;
 
 typedef struct fa_b200_bwd_args {
@@ -134,6 +136,7 @@ typedef struct fa_b200_bwd_args {
   float p_dropout;
   uint64_t philox_seed, philox_offset;
   const uint64_t* rng_state;
+  int32_t sm_margin;                      /* FA3 `sm_margin` (see fa_b200_fwd_args) */
 } fa_b200_bwd_args;
 
 /* ---- forward ---- */
@@ -183,6 +186,10 @@ size_t fa_b200_sizeof_append_args(void);
  *      `height` rows of `width_bytes`; pitches in bytes.  Asynchronous on `stream`. */
 int fa_b200_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
                            size_t height, int32_t kind, fa_b200_stream_t stream);
+
+/* writes {seed, offset} into a device (2,) uint64 buffer on `stream`: the `rng_state` tensor mha_fwd returns
+ * (flash_api.cpp:501-517), filled without a host->device copy */
+int fa_b200_write_rng_state(uint64_t* dst, uint64_t seed, uint64_t offset, fa_b200_stream_t stream);
 
 /* ---- helpers ---- */
 int fa_b200_num_splits_heuristic(int batch_nheads_mblocks, int num_sms, int num_n_blocks, int max_splits);

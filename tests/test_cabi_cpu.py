@@ -1,6 +1,8 @@
 """CPU-side checks: the C-ABI library builds/loads without a GPU and exports every symbol that
 include/fa_b200.h declares; host-only helpers behave like the reference's."""
 import ctypes as C
+
+import pytest
 import os
 import re
 
@@ -181,3 +183,42 @@ def test_varlen_backward_workspace_grows_with_total_q_not_batch_times_max(fa_lib
     assert ws > 0
     assert ws <= h * rows * (d + 2) * 4 + (b * h * (max_s // 128) * 2 * 4) + 4096      # ~ 2 GB, was ~ 69 GB
     assert ws < 0.05 * (b * h * max_s * d * 4)
+
+
+def test_compiled_operator_module_surface_and_host_checks():
+    """The compiled `flash_attn_2_cuda` module (csrc/ext/*.cpp, pybind11 + TORCH_LIBRARY) imports without a GPU, exports the
+    reference's five entry points with their positional arities (flash_api.cpp:1535-1542; 2.8.3: 21-argument varlen_fwd,
+    2.8.4: 22 with num_splits) and raises the reference's messages from its C++ argument checks before touching CUDA."""
+    import inspect
+
+    import torch
+
+    import flash_attention_b200 as fab
+
+    mod = fab.install()
+    import flash_attn_2_cuda as installed
+
+    assert installed is mod and mod.__file__.endswith(".so") and mod.__name__ == "flash_attn_2_cuda"
+    for name in ("fwd", "varlen_fwd", "bwd", "varlen_bwd", "fwd_kvcache", "fwd_fp8", "fwd_ex", "fwd_combine", "plan_kvcache"):
+        assert callable(getattr(mod, name)), name
+    doc = mod.varlen_fwd.__doc__
+    assert "num_splits: typing.SupportsInt" in doc or "num_splits: int" in doc
+    q = torch.zeros(1, 8, 2, 16, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="generator` argument is no longer supported"):   # tests/test_flash_attn.py:2650
+        mod.fwd(q, q, q, None, None, 0.0, 0.25, True, -1, -1, 0.0, False, torch.empty(1))
+    with pytest.raises(RuntimeError, match="Input tensor must be on CUDA device"):
+        mod.fwd(q, q, q, None, None, 0.0, 0.25, True, -1, -1, 0.0, False, None)
+    with pytest.raises(RuntimeError, match="only support fp16 and bf16"):
+        mod.fwd(q.float(), q.float(), q.float(), None, None, 0.0, 0.25, True, -1, -1, 0.0, False, None)
+    # the FA3 operator library is registered by the same shared object (hopper/flash_api.cpp:1673-1768)
+    ops = torch.ops.flash_attn_3
+    for name in ("fwd", "bwd", "fwd_combine", "get_scheduler_metadata"):
+        assert hasattr(ops, name)
+    schema = str(ops.fwd.default._schema)
+    assert "Tensor? q_descale=None" in schema and "int sm_margin=0" in schema and "Tensor? page_table=None" in schema
+    # host-only planner through the compiled module (same numbers as the C ABI)
+    assert mod.plan_kvcache(64, 1, 65536, 32, 4, 128, 256, False, -1, -1)[1] == 8
+    fab.install_fa3()
+    import flash_attn_3._C as c3   # what hopper/flash_attn_interface.py:24 does
+
+    assert c3 is mod
