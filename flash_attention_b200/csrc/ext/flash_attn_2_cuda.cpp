@@ -25,23 +25,14 @@
 namespace fa_ext {
 
 // ------------------------------------------------------------------------------------------------ helpers
-at::Tensor zero_rng_state(const at::Device& dev) {
-  // one shared, never-written (2,) int64 zero state per device for p_dropout == 0 (saves a fill kernel per call)
-  static auto* cache = new std::array<at::Tensor, 64>();
-  static std::mutex mu;
-  const int idx = dev.index() < 0 ? at::cuda::current_device() : dev.index();
-  std::lock_guard<std::mutex> lock(mu);
-  if (idx >= 64) return at::zeros({2}, at::TensorOptions().dtype(at::kLong).device(dev));
-  if (!(*cache)[idx].defined()) (*cache)[idx] = at::zeros({2}, at::TensorOptions().dtype(at::kLong).device(dev));
-  return (*cache)[idx];
-}
-
 // Philox (seed, offset) of this call from the default CUDA generator, advanced like the reference does
 // (flash_api.cpp:505-517: counter_offset = b * h * 32); returns the `rng_state` tensor the reference returns.
 at::Tensor dropout_state(float p_dropout, int64_t b, int64_t h, const at::Device& dev, uint64_t* seed, uint64_t* offset) {
   TORCH_CHECK(p_dropout >= 0.f && p_dropout < 1.f, "p_dropout must be in [0, 1)");
   *seed = *offset = 0;
-  if (p_dropout == 0.f) return zero_rng_state(dev);
+  // p_dropout == 0: a fresh, uninitialised (2,) int64 tensor, exactly as the reference returns (flash_api.cpp:501-503); it
+  // must be a new tensor per call: the reference's custom ops (and ours) may not return aliases of earlier outputs
+  if (p_dropout == 0.f) return at::empty({2}, at::TensorOptions().dtype(at::kLong).device(dev));
   auto gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(std::nullopt, at::cuda::detail::getDefaultCUDAGenerator());
   at::PhiloxCudaState st;
   {
@@ -54,18 +45,6 @@ at::Tensor dropout_state(float p_dropout, int64_t b, int64_t h, const at::Device
   auto rng = at::empty({2}, at::TensorOptions().dtype(at::kLong).device(dev));
   check_rc(fa_b200_write_rng_state(reinterpret_cast<uint64_t*>(rng.data_ptr()), *seed, *offset, cur_stream()));
   return rng;
-}
-
-// the zero-element `p` returned when return_softmax is off: one shared tensor per (device, dtype)
-at::Tensor empty_p(const at::Tensor& q) {
-  static auto* cache = new std::array<at::Tensor, 128>();
-  static std::mutex mu;
-  const int dev = q.device().index() < 0 ? at::cuda::current_device() : q.device().index();
-  if (dev >= 64) return empty_like_dtype(q);
-  const int idx = dev * 2 + (q.scalar_type() == at::kBFloat16 ? 1 : 0);
-  std::lock_guard<std::mutex> lock(mu);
-  if (!(*cache)[idx].defined()) (*cache)[idx] = empty_like_dtype(q);
-  return (*cache)[idx];
 }
 
 void set_alibi(fa_b200_fwd_args& a, const std::optional<at::Tensor>& alibi, int64_t b, int64_t h) {
@@ -133,7 +112,7 @@ std::vector<at::Tensor> fwd(const at::Tensor& q, const at::Tensor& k, const at::
     out = at::empty_like(q);
   }
   auto lse = at::empty({b, h, sq}, q.options().dtype(at::kFloat));
-  at::Tensor p = empty_p(q);
+  at::Tensor p = empty_like_dtype(q);
   fa_b200_fwd_args a = {};
   auto rng_state = dropout_state(float(p_dropout), b, h, q.device(), &a.philox_seed, &a.philox_offset);
   a.p_dropout = float(p_dropout);
@@ -308,7 +287,7 @@ std::vector<at::Tensor> varlen_fwd(const at::Tensor& q, const at::Tensor& k, con
     out = at::empty_like(q);
   }
   auto lse = at::empty({h, total_q}, q.options().dtype(at::kFloat));
-  at::Tensor p = empty_p(q);
+  at::Tensor p = empty_like_dtype(q);
   fa_b200_fwd_args a = {};
   if (p_dropout > 0.0)
     TORCH_CHECK(!paged && !seqused_k.has_value() && !seqused_q.has_value(), "dropout is not supported together with paged KV / seqused");
@@ -360,6 +339,7 @@ std::vector<at::Tensor> varlen_fwd(const at::Tensor& q, const at::Tensor& k, con
   a.num_splits = 1;
   a.entry = FA_B200_ENTRY_VARLEN;
   set_alibi(a, alibi_slopes_, b, h);
+  auto ws = fwd_workspace(a, q);   // the (b + 1)-entry m-block prefix sum of the persistent kernel's work list
   check_rc(fa_b200_mha_varlen_fwd(&a, cur_stream()));
   return {out, lse, p, rng_state};
 }

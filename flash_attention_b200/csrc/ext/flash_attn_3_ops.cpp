@@ -112,12 +112,13 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> fa3_fwd(
     out = !varlen_q ? at::empty({b, sq, h, d}, q.options().dtype(out_type)) : at::empty({total_q, h, d}, q.options().dtype(out_type));
   }
   at::Tensor lse = !varlen_q ? at::empty({b, h, sq}, q.options().dtype(at::kFloat)) : at::empty({h, total_q}, q.options().dtype(at::kFloat));
-  at::Tensor none = at::empty({0}, q.options().dtype(at::kFloat));
-  if (total_q == 0) return {out, lse, none, none};
+  // out_accum / softmax_lse_accum are internal scratch here: two distinct empty placeholders (returns may not alias)
+  at::Tensor none = at::empty({0}, q.options().dtype(at::kFloat)), none2 = at::empty({0}, q.options().dtype(at::kFloat));
+  if (total_q == 0) return {out, lse, none, none2};
   if (sk == 0) {
     out.zero_();
     lse.fill_(std::numeric_limits<float>::infinity());
-    return {out, lse, none, none};
+    return {out, lse, none, none2};
   }
   if (rotary_cos_.has_value()) {
     TORCH_CHECK(k_new_.has_value(), "If rotary cos/sin are provided, new key / value to be appended to KV cache must also be provided");
@@ -234,6 +235,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> fa3_fwd(
   if (varlen_q) {
     a.entry = FA_B200_ENTRY_VARLEN;
     a.num_splits = 1;
+    ws = fwd_workspace(a, q);
     check_rc(fa_b200_mha_varlen_fwd(&a, cur_stream()));
   } else if (cache_call) {
     a.entry = FA_B200_ENTRY_KVCACHE;
@@ -244,7 +246,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> fa3_fwd(
     ws = fwd_workspace(a, q);
     check_rc(fa_b200_mha_fwd(&a, cur_stream()));
   }
-  return {out, lse, none, none};
+  return {out, lse, none, none2};
 }
 
 // mha_bwd (hopper/flash_api.cpp:1267-1567): dq / dk / dv are written in place (allocated when absent); returns
@@ -298,11 +300,11 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor> fa3_bwd(
   at::Tensor dq = alloc(dq_, q, "dq"), dk = alloc(dk_, k, "dk"), dv = alloc(dv_, v, "dv");
   at::Tensor softmax_d = !varlen ? at::empty({b, h, round128(sq)}, q.options().dtype(at::kFloat))
                                  : at::empty({h, total_q + 128 * b}, q.options().dtype(at::kFloat));
-  at::Tensor none = at::empty({0}, q.options().dtype(at::kFloat));
-  if (total_q == 0) return {softmax_d, none, none, none, none};
+  auto empty_f = [&] { return at::empty({0}, q.options().dtype(at::kFloat)); };
+  if (total_q == 0) return {softmax_d, empty_f(), empty_f(), empty_f(), empty_f()};
   if (sk == 0 || total_k == 0) {
     dq.zero_(); dk.zero_(); dv.zero_(); softmax_d.zero_();
-    return {softmax_d, none, none, none, none};
+    return {softmax_d, empty_f(), empty_f(), empty_f(), empty_f()};
   }
   fa_b200_bwd_args a = {};
   a.dout = dout.data_ptr(); a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.out = out.data_ptr();
@@ -330,7 +332,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor> fa3_bwd(
   a.workspace = ws.data_ptr();
   a.workspace_bytes = nbytes;
   check_rc(varlen ? fa_b200_mha_varlen_bwd(&a, cur_stream()) : fa_b200_mha_bwd(&a, cur_stream()));
-  return {softmax_d, none, none, none, none};
+  return {softmax_d, empty_f(), empty_f(), empty_f(), empty_f()};
 }
 
 // mha_combine (hopper/flash_api.cpp:1570-1670): out_partial (splits, b, s, h, d) fp32, lse_partial (splits, b, s, h) fp32

@@ -221,7 +221,10 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     if (pl->has_left) est_blocks = std::min(est_blocks, cdiv(wl + std::max(wr, 0) + 256, 128));
     // measured (profiles/r01_v3_sweep_tiles.txt): causal forward is faster with 1-tile CTAs up to s = 16k
     // (est_blocks <= 64), non-causal only up to s = 1k (est_blocks <= 8)
-    const int limit = pl->has_right ? 64 : 8;
+    // round 2: with the persistent loop (prologue / epilogue overlapped, per-tile block ranges) the 2-tile kernel also
+    // wins on long causal problems; FA_B200_FWD_TILE_LIMIT_CAUSAL overrides the crossover for experiments
+    static const int causal_limit = [] { const char* e = getenv("FA_B200_FWD_TILE_LIMIT_CAUSAL"); return e ? atoi(e) : 8; }();
+    const int limit = pl->has_right ? causal_limit : 8;
     pl->tiles = (a.seqlen_q * (g > 1 && is_pow2(g) ? g : 1) <= 128 || est_blocks <= limit) ? 1 : 2;
     if (const char* e = getenv("FA_B200_FWD_TILES")) { if (e[0] == '1') pl->tiles = 1; if (e[0] == '2') pl->tiles = 2; }
     if (pl->kD == 256) pl->tiles = 1;  // S (128) + O (256) TMEM columns: one tile per CTA (forward only)
@@ -274,6 +277,8 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     pl->ws_bytes = rows * pl->kD * sizeof(float) + rows * sizeof(float);
     pl->ws_bytes = (pl->ws_bytes + 255) & ~size_t(255);
   }
+  // packed varlen: the (b + 1)-entry m-block prefix sum the persistent kernel enumerates its work items with
+  if (a.cu_seqlens_q) pl->ws_bytes = ((size_t(a.b) + 1) * sizeof(int) + 255) & ~size_t(255);
   return 0;
 }
 
@@ -304,8 +309,9 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   FwdPlan pl;
   if (!a.q || !a.k || !a.v || !a.out || !a.softmax_lse) return set_error("q, k, v, out, softmax_lse must be non-null");
   if (int rc = plan_fwd(a, mode, &pl)) return rc;
-  if (pl.num_splits > 1 && (!a.workspace || a.workspace_bytes < pl.ws_bytes))
-    return set_error("workspace too small for split-KV (query fa_b200_fwd_workspace_bytes)");
+  if (pl.ws_bytes > 0 && (!a.workspace || a.workspace_bytes < pl.ws_bytes))
+    return set_error(pl.num_splits > 1 ? "workspace too small for split-KV (query fa_b200_fwd_workspace_bytes)"
+                                       : "workspace too small for the varlen work list (query fa_b200_fwd_workspace_bytes)");
   if (a.seqlen_q == 0 || (mode == kVarlen && a.total_q == 0)) return 0;
 
   const bool fp8 = a.dtype == FA_B200_FP8_E4M3;
@@ -366,7 +372,7 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   kp.page_size = a.block_table ? a.page_block_size : 0;
   kp.num_splits = pl.num_splits;
   kp.has_left = pl.has_left; kp.has_right = pl.has_right; kp.wl = pl.wl; kp.wr = pl.wr;
-  kp.reverse_m = pl.has_right ? 1 : 0;
+  kp.reverse_m = pl.has_right ? 1 : 0;   // causal: the last m-blocks see the most keys -> dispatched first
   if (a.softcap > 0.f) {  // s' = tanh(s * scale / softcap) * softcap  (flash_api.cpp:130-134)
     kp.softcap_pre = a.softmax_scale / a.softcap;
     kp.scale = a.softcap;
@@ -381,14 +387,39 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     kp.o_accum = reinterpret_cast<float*>(a.workspace);
     kp.lse_accum = kp.o_accum + rows * pl.kD;
   }
-  dim3 grid(pl.num_m_blocks, a.h / gp, a.b * pl.num_splits);
-  // masked work is uneven across m-blocks: dispatch every head's heavy m-blocks first (m-block = slowest grid dimension)
+  // Persistent grid: one CTA per SM (two for the 1-tile configuration), fewer if there is less work, `sm_margin` SMs left
+  // free (FA3).  Work items are enumerated inside the kernel (fwd_decode_work): heavy m-blocks first within groups of head
+  // slots whose K/V fit L2 together; packed varlen batches through the m-block prefix sum written by the prepare kernel.
   kp.num_m_blocks = pl.num_m_blocks;
-  if (const int c = sched_chunk_fwd(pl.has_left || pl.has_right);
-      c > 0 && pl.num_m_blocks > c && int64_t(grid.y) * grid.z <= 65535) {   // short problems keep the plain grid
-    kp.sched_lpt = c;
-    grid = dim3(c, grid.y * grid.z, (pl.num_m_blocks + c - 1) / c);
+  const int nslots = a.h / gp;
+  const int64_t hz_total = int64_t(nslots) * a.b * pl.num_splits;
+  {
+    const double kv_bytes = 2.0 * double(a.block_table ? a.seqlen_k : a.seqlen_k) * a.d * esz;   // K + V of one kv head
+    int kv_heads = int(std::max(1.0, std::floor(32.0 * 1024 * 1024 / std::max(kv_bytes, 1.0))));
+    int64_t grp = int64_t(kv_heads) * (g / gp);   // head slots that share those kv heads
+    if (const char* e = getenv("FA_B200_SCHED_GROUP")) grp = atoi(e);
+    grp = std::max<int64_t>(1, std::min<int64_t>(grp, hz_total));
+    kp.sched_group = int(grp);
   }
+  const int64_t total_items = int64_t(pl.num_m_blocks) * hz_total;
+  if (total_items > INT32_MAX) return set_error("too many work items");
+  kp.total_items = int(total_items);
+  const int ctas_per_sm = pl.tiles == 1 && pl.kD != 256 ? 2 : 1;
+  int sms = num_sms() - std::max(0, a.sm_margin);
+  if (sms < 1) sms = 1;
+  int64_t ctas = int64_t(sms) * ctas_per_sm;
+  if (a.cu_seqlens_q) {
+    int* prefix = reinterpret_cast<int*>(a.workspace);
+    fa_fwd_varlen_prepare<<<1, 256, 0, stream>>>(a.cu_seqlens_q, a.seqused_q, a.b, gp, 128 * pl.tiles, prefix);
+    g_launch_count++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(std::string("fa_fwd_varlen_prepare launch: ") + cudaGetErrorString(e));
+    kp.varlen_prefix = prefix;
+    ctas = std::min<int64_t>(ctas, std::max<int64_t>(1, total_items));   // upper bound: max_seqlen m-blocks per batch
+  } else {
+    ctas = std::min<int64_t>(ctas, total_items);
+  }
+  dim3 grid(unsigned(ctas), 1, 1);
   int rc;
   if (fp8) {
     rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream, pl.tiles);

@@ -42,13 +42,13 @@ __device__ unsigned int g_bwd2_span_n;
 __device__ unsigned long long g_bwd2_ts[2 * 16 * 32];   // [rank][iteration - 8][event]
 #define TS(ev)                                                                                          \
   do {                                                                                                  \
-    if (pair == 0 && hk == 0 && bidb == 0 && it >= 8 && it < 24)                      \
+    if (ts_on && it >= 8 && it < 24)                                                   \
       g_bwd2_ts[(int(rank) * 16 + (it - 8)) * 32 + (ev)] = clock64();                                    \
   } while (0)
 // once-per-CTA stamps (prologue / epilogue): slot [rank][15][ev]
 #define TSX(ev)                                                                                         \
   do {                                                                                                  \
-    if (pair == 0 && hk == 0 && bidb == 0) g_bwd2_ts[(int(rank) * 16 + 15) * 32 + (ev)] = clock64();      \
+    if (blockIdx.x < 2) g_bwd2_ts[(int(rank) * 16 + 15) * 32 + (ev)] = clock64();                         \
   } while (0)
 #else
 #define TS(ev) do {} while (0)
@@ -70,45 +70,76 @@ struct Bwd2Cfg {
   static constexpr int kSDX = kSDQ + 16384;      // export staging: the dS^T rows owed to the peer (128 keys x 64 queries)
   static constexpr int kSStat = kSDX + 16384;    // lse_log2[2][128], dpsum[2][128]
   static constexpr int kSBar = kSStat + 2048;
-  static constexpr int kNumBars = 26;
+  static constexpr int kNumBars = 29;
   static constexpr int kSmemBytes = kSBar + 8 * kNumBars + 16;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
+// One work item of the persistent pair kernel: a pair of adjacent 128-key blocks of one (batch, kv head).
+struct Bwd2Work {
+  int pair, hk, bidb;
+  int q_off, sq_b, k_off, sk_b, pkey0, shift;
+  int m_min, n_m, n_iter;
+};
+// Item index -> work item; false if the pair lies beyond its sequence (varlen) or the index is past the end.  Order:
+// groups of `sched_group` (kv head, batch) combinations whose Q / dO / dq_accum stream shares L2; inside a group the pair
+// index is the slow dimension, ASCENDING: with a causal mask the low pairs are the heavy ones (longest-processing-time
+// first), and the deterministic mode's "lower pairs add first" chains (dq_semaphore) only ever wait for items that were
+// dealt out earlier, which keeps them deadlock-free under static scheduling.
+__device__ __forceinline__ bool bwd2_decode_work(const BwdKernelParams& p, int L, Bwd2Work& w) {
+  const int hz_total = p.h_k * p.b;
+  const int per_group = p.num_pairs * p.sched_group;
+  const int grp = L / per_group;
+  const int within = L - grp * per_group;
+  int gsz = hz_total - grp * p.sched_group;
+  gsz = gsz < p.sched_group ? gsz : p.sched_group;
+  w.pair = within / gsz;
+  const int hz = grp * p.sched_group + (within - w.pair * gsz);
+  w.hk = hz % p.h_k;
+  w.bidb = hz / p.h_k;
+  w.q_off = 0; w.sq_b = p.sq; w.k_off = 0; w.sk_b = p.sk;
+  if (p.cu_seqlens_q) { w.q_off = p.cu_seqlens_q[w.bidb]; w.sq_b = p.cu_seqlens_q[w.bidb + 1] - w.q_off; }
+  if (p.cu_seqlens_k) { w.k_off = p.cu_seqlens_k[w.bidb]; w.sk_b = p.cu_seqlens_k[w.bidb + 1] - w.k_off; }
+  w.pkey0 = w.pair * 256;
+  if (w.pkey0 >= w.sk_b) return false;  // the whole pair lies beyond this sequence
+  w.shift = w.sk_b - w.sq_b;
+  const int m_total = (w.sq_b + 127) / 128;
+  // query-block range of the PAIR = union of its key blocks' ranges; a block outside its own range sees a fully
+  // masked tile (P = dS = 0), which keeps the two CTAs in lock step
+  int m_min = 0, m_max = m_total;
+  if (p.has_right) {
+    const int lo = w.pkey0 - w.shift - p.wr;
+    m_min = lo <= 0 ? 0 : lo / 128;
+  }
+  if (p.has_left) {
+    const int last_key0 = w.pkey0 + 128 < w.sk_b ? w.pkey0 + 128 : w.pkey0;
+    const int hi = last_key0 + 127 - w.shift + p.wl;
+    const int nb = hi < 0 ? 0 : hi / 128 + 1;
+    m_max = nb < m_max ? nb : m_max;
+  }
+  w.m_min = m_min;
+  w.n_m = m_max > m_min ? m_max - m_min : 0;
+  w.n_iter = w.n_m * p.g;
+  return true;
+}
+
+// PERSISTENT: the grid is one CTA pair (cluster) per two SMs; every pair loops over work items (bwd2_decode_work), dealt
+// out in snake order (round r: cluster c takes item r*G + c, or r*G + G-1-c on odd rounds).  Barrier phases, the Q / dO
+// stages and TMEM stay live across items; what an item needs from its predecessor is tracked by two extra barriers
+// (ACC_FREE: dV / dK accumulators read out by both CTAs' epilogues; STAGE_FREE: the epilogue's dV / dK staging -- the dS^T and
+// K^T buffers, idle at the end of an item -- has been read by its TMA stores in both CTAs).  K / V are free as soon as the
+// item's last MMA is done (DKV_F), so the next item's K / V / Q / dO loads and its first S^T, dP^T run under the current
+// item's dK / dV epilogue; only its K^T panel (first needed by dQ, late in the first tile) waits for STAGE_FREE.
 template <typename T, bool kSoftcap, bool kDropout>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Bwd2Cfg::kThreads, 1)
 fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   using Cfg = Bwd2Cfg;
   constexpr int kD = 128;
   const uint32_t rank = cluster_ctarank();
-  // grid (2 * pairs, h_k, b): head-major; or with sched_lpt = c > 0 (2c, h_k * b, ceil(pairs / c)): chunks of c adjacent
-  // pairs of one head stay together (they share Q/dO through L2), chunk index slowest = heavy (causal) chunks of all heads first
-  const int pair = p.sched_lpt ? int(blockIdx.z) * p.sched_lpt + int(blockIdx.x >> 1) : int(blockIdx.x >> 1);
-  const int hk = p.sched_lpt ? blockIdx.y % p.h_k : blockIdx.y, bidb = p.sched_lpt ? blockIdx.y / p.h_k : blockIdx.z;
-  int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
-  if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
-  if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
-  const int pkey0 = pair * 256;
-  if (pkey0 >= sk_b) return;  // the whole pair lies beyond this sequence: both CTAs leave before any cluster operation
-  const int key0 = pkey0 + 128 * int(rank);
-  const int n_block = 2 * pair + int(rank);
-  const int shift = sk_b - sq_b;
-  const int m_total = (sq_b + 127) / 128;
-  // query-block range of the PAIR = union of its key blocks' ranges; a block outside its own range sees a fully
-  // masked tile (P = dS = 0), which keeps the two CTAs in lock step
-  int m_min = 0, m_max = m_total;
-  if (p.has_right) {
-    const int lo = pkey0 - shift - p.wr;
-    m_min = lo <= 0 ? 0 : lo / 128;
-  }
-  if (p.has_left) {
-    const int last_key0 = pkey0 + 128 < sk_b ? pkey0 + 128 : pkey0;
-    const int hi = last_key0 + 127 - shift + p.wl;
-    const int nb = hi < 0 ? 0 : hi / 128 + 1;
-    m_max = nb < m_max ? nb : m_max;
-  }
-  const int n_m = m_max > m_min ? m_max - m_min : 0;
-  const int n_iter = n_m * p.g;
+  const int G = int(gridDim.x >> 1), cl = int(blockIdx.x >> 1);
+  const int total_items = p.total_items;
+  const int rounds = (total_items + G - 1) / G;
+  auto item_of_round = [&](int r) { return r * G + ((r & 1) ? (G - 1 - cl) : cl); };
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -122,7 +153,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   // F_*: "operand landed" barriers, live in the LEADER (rank 0) and collect the TMA bytes of both CTAs
   // E_*: "operand consumed" barriers, one per CTA, signalled by multicast tcgen05.commit
   enum { F_KV = 0, F_QB = 1, F_DOB = 2, F_DOG = 3, F_QG = 4, E_QB = 5, E_DOB = 6, E_DOG = 7, E_QG = 8, F_ST0 = 9,
-         F_ST1 = 10, S_F = 11, DP_F = 12, P_F = 13, DS_F = 14, DQ_F = 15, DQ_E = 16, DKV_F = 17, DS_IN = 18, DS_PEER = 19, T_DV = 20, T_S = 21, T_DK = 22, T_DQ = 23, T_DP = 24, S_RD = 25 };
+         F_ST1 = 10, S_F = 11, DP_F = 12, P_F = 13, DS_F = 14, DQ_F = 15, DQ_E = 16, DKV_F = 17, DS_IN = 18, DS_PEER = 19, T_DV = 20, T_S = 21, T_DK = 22, T_DQ = 23, T_DP = 24, S_RD = 25, ACC_FREE = 26, STAGE_FREE = 27, F_KT = 28 };
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSBar + 8 * Cfg::kNumBars);
@@ -161,6 +192,10 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
 #endif
       mbar_init(bar(S_RD), 16);     // leader only: all compute warps of the pair have read S^T out of TMEM
       mbar_init(bar(DS_PEER), 1);   // leader only: the peer's sDS is complete (relayed by the peer's warp 12)
+      mbar_init(bar(ACC_FREE), 16); // leader only: all compute warps of the pair have read dV / dK out of TMEM (item epilogue)
+      mbar_init(bar(STAGE_FREE), 2); // per CTA: the dV / dK staging (the dS^T and K^T buffers, idle at the end of an item) of BOTH
+                                     // CTAs has been read by the epilogue's TMA stores (one arrive from each CTA's epilogue thread)
+      mbar_init(bar(F_KT), 1);       // leader: the K^T panels of both CTAs have landed (loaded after STAGE_FREE, needed by dQ only)
       fence_barrier_init();
     }
     __syncwarp();
@@ -180,55 +215,79 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     // ================================================================ TMA producer (one per CTA)
     if (warp == 13) {
       if (elect_one()) {
-        const int bk = p.cu_seqlens_k ? 0 : bidb, bq = p.cu_seqlens_q ? 0 : bidb;
         const uint32_t fKV = mapa_rank(bar(F_KV), 0), fQB = mapa_rank(bar(F_QB), 0), fDOB = mapa_rank(bar(F_DOB), 0);
         const uint32_t fDOG = mapa_rank(bar(F_DOG), 0), fQG = mapa_rank(bar(F_QG), 0);
         const int dcol = 64 * int(rank);
-        if (rank == 0) mbar_arrive_expect_tx(bar(F_KV), 2 * 3 * 32768);
+        int git = 0;      // tiles processed so far by this pair, over all its items: phase of the per-tile barriers
+        int kitem = 0;    // items with work processed so far: phase of F_KV / F_KT / DKV_F / STAGE_FREE
+        for (int r = 0; r < rounds; ++r) {
+          const int L = item_of_round(r);
+          Bwd2Work w;
+          if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+          const int bk = p.cu_seqlens_k ? 0 : w.bidb, bq = p.cu_seqlens_q ? 0 : w.bidb;
+          const int key0 = w.pkey0 + 128 * int(rank);
+          // this pair's K / V tiles are free once the previous item's last MMA is done (multicast commit)
+          if (kitem > 0) mbar_wait(bar(DKV_F), (kitem - 1) & 1, 404);
+          if (rank == 0) mbar_arrive_expect_tx(bar(F_KV), 2 * 2 * 32768);
 #pragma unroll
-        for (int pn = 0; pn < 2; ++pn) {
-          tma_load_4d_pair(sK + pn * 16384, &p.tm_k, fKV, pn * 64, k_off + key0, hk, bk);
-          tma_load_4d_pair(sV + pn * 16384, &p.tm_v, fKV, pn * 64, k_off + key0, hk, bk);
-          tma_load_4d_pair(sKt + pn * 16384, &p.tm_k, fKV, dcol, k_off + pkey0 + 128 * pn, hk, bk);
-        }
-        for (int it = 0; it < n_iter; ++it) {
-          const int hq = hk * p.g + it / n_m;
-          const int m = m_min + it % n_m;
-          const int st = it & 1;
-          const int qrow = q_off + m * 128;
-          const int64_t srow = ws_rows(p.cu_seqlens_q, bidb, p.h, hq, p.sq_r, p.ws_head_pitch).stat_base + m * 128;
-          const uint32_t free_par = (it & 1) ^ 1;
-          mbar_wait(bar(E_QB), free_par, 400);     // S^T of the previous iteration has read sQb
-          if (rank == 0) mbar_arrive_expect_tx(bar(F_QB), 2 * 16384);
-          tma_load_4d_pair(sQb, &p.tm_q64, fQB, 0, qrow + 64 * int(rank), hq, bq);
-          tma_load_4d_pair(sQb + 8192, &p.tm_q64, fQB, 64, qrow + 64 * int(rank), hq, bq);
-          // row statistics of this query block (all 128 rows) for this CTA's compute warps
-          mbar_arrive_expect_tx(bar(F_ST0 + st), 1024);
-          bulk_load_1d(sStat + st * 512, p.lse_log2 + srow, 512, bar(F_ST0 + st));
-          bulk_load_1d(sStat + 1024 + st * 512, p.dpsum + srow, 512, bar(F_ST0 + st));
-          mbar_wait(bar(E_DOB), free_par, 401);
-          if (rank == 0) mbar_arrive_expect_tx(bar(F_DOB), 2 * 16384);
-          tma_load_4d_pair(sDOb, &p.tm_do64, fDOB, 0, qrow + 64 * int(rank), hq, bq);
-          tma_load_4d_pair(sDOb + 8192, &p.tm_do64, fDOB, 64, qrow + 64 * int(rank), hq, bq);
-          mbar_wait(bar(E_DOG), free_par, 402);
-          if (rank == 0) mbar_arrive_expect_tx(bar(F_DOG), 2 * 16384);
-          tma_load_4d_pair(sDOg, &p.tm_do, fDOG, dcol, qrow, hq, bq);
-          mbar_wait(bar(E_QG), free_par, 403);
-          if (rank == 0) mbar_arrive_expect_tx(bar(F_QG), 2 * 16384);
-          tma_load_4d_pair(sQg, &p.tm_q, fQG, dcol, qrow, hq, bq);
+          for (int pn = 0; pn < 2; ++pn) {
+            tma_load_4d_pair(sK + pn * 16384, &p.tm_k, fKV, pn * 64, w.k_off + key0, w.hk, bk);
+            tma_load_4d_pair(sV + pn * 16384, &p.tm_v, fKV, pn * 64, w.k_off + key0, w.hk, bk);
+          }
+          for (int it = 0; it < w.n_iter; ++it, ++git) {
+            // (first tile: the K^T panel is loaded behind the Q rows below.  It doubles as the dK staging of the previous
+            // item's epilogue, so it waits for those TMA stores in both CTAs; dQ, its first consumer, is a tile's work away)
+            const int hq = w.hk * p.g + it / w.n_m;
+            const int m = w.m_min + it % w.n_m;
+            const int st = git & 1;
+            const int qrow = w.q_off + m * 128;
+            const int64_t srow = ws_rows(p.cu_seqlens_q, w.bidb, p.h, hq, p.sq_r, p.ws_head_pitch).stat_base + m * 128;
+            const uint32_t free_par = (git & 1) ^ 1;
+            mbar_wait(bar(E_QB), free_par, 400);     // S^T of the previous tile has read sQb
+            if (rank == 0) mbar_arrive_expect_tx(bar(F_QB), 2 * 16384);
+            tma_load_4d_pair(sQb, &p.tm_q64, fQB, 0, qrow + 64 * int(rank), hq, bq);
+            tma_load_4d_pair(sQb + 8192, &p.tm_q64, fQB, 64, qrow + 64 * int(rank), hq, bq);
+            if (it == 0) {
+              if (kitem > 0) mbar_wait(bar(STAGE_FREE), (kitem - 1) & 1, 405);
+              if (rank == 0) mbar_arrive_expect_tx(bar(F_KT), 2 * 32768);
+              const uint32_t fKT = mapa_rank(bar(F_KT), 0);
+#pragma unroll
+              for (int pn = 0; pn < 2; ++pn)
+                tma_load_4d_pair(sKt + pn * 16384, &p.tm_k, fKT, dcol, w.k_off + w.pkey0 + 128 * pn, w.hk, bk);
+              ++kitem;
+            }
+            // row statistics of this query block (all 128 rows) for this CTA's compute warps
+            mbar_arrive_expect_tx(bar(F_ST0 + st), 1024);
+            bulk_load_1d(sStat + st * 512, p.lse_log2 + srow, 512, bar(F_ST0 + st));
+            bulk_load_1d(sStat + 1024 + st * 512, p.dpsum + srow, 512, bar(F_ST0 + st));
+            mbar_wait(bar(E_DOB), free_par, 401);
+            if (rank == 0) mbar_arrive_expect_tx(bar(F_DOB), 2 * 16384);
+            tma_load_4d_pair(sDOb, &p.tm_do64, fDOB, 0, qrow + 64 * int(rank), hq, bq);
+            tma_load_4d_pair(sDOb + 8192, &p.tm_do64, fDOB, 64, qrow + 64 * int(rank), hq, bq);
+            mbar_wait(bar(E_DOG), free_par, 402);
+            if (rank == 0) mbar_arrive_expect_tx(bar(F_DOG), 2 * 16384);
+            tma_load_4d_pair(sDOg, &p.tm_do, fDOG, dcol, qrow, hq, bq);
+            mbar_wait(bar(E_QG), free_par, 403);
+            if (rank == 0) mbar_arrive_expect_tx(bar(F_QG), 2 * 16384);
+            tma_load_4d_pair(sQg, &p.tm_q, fQG, dcol, qrow, hq, bq);
+          }
         }
       }
       __syncwarp();
     }
 #if FA_BWD2_TS
     else if (warp == 14) {
-      if (rank == 0 && lane == 0) {   // completion times of the MMA groups (leader clock)
-        for (int it = 0; it < n_iter; ++it) {
-          mbar_wait(bar(T_DV), it & 1, 800); TS(21);
-          if (it + 1 < n_iter) { mbar_wait(bar(T_S), it & 1, 801); TS(22); }
-          mbar_wait(bar(T_DK), it & 1, 802); TS(23);
-          mbar_wait(bar(T_DQ), it & 1, 803); TS(24);
-          if (it + 1 < n_iter) { mbar_wait(bar(T_DP), it & 1, 804); TS(25); }
+      if (rank == 0 && lane == 0 && blockIdx.x < 2) {   // completion times of the MMA groups (leader clock), first item only
+        Bwd2Work w;
+        const bool ts_on = true;
+        if (bwd2_decode_work(p, item_of_round(0), w)) {
+          for (int it = 0; it < w.n_iter; ++it) {
+            mbar_wait(bar(T_DV), it & 1, 800); TS(21);
+            if (it + 1 < w.n_iter) { mbar_wait(bar(T_S), it & 1, 801); TS(22); }
+            mbar_wait(bar(T_DK), it & 1, 802); TS(23);
+            mbar_wait(bar(T_DQ), it & 1, 803); TS(24);
+            if (it + 1 < w.n_iter) { mbar_wait(bar(T_DP), it & 1, 804); TS(25); }
+          }
         }
       }
       __syncwarp();
@@ -236,7 +295,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
 #endif
     // ================================================================ MMA issuer: one thread of the LEADER CTA
     else if (warp == 12) {
-      if (rank == 0 && n_iter > 0 && elect_one()) {
+      if (rank == 0 && elect_one()) {
         constexpr uint32_t fmt = Elt<T>::kFmt;
         constexpr uint32_t id_s = make_idesc(fmt, fmt, 0, 0, 256, 128);    // S^T, dP^T : K-major A and B
         constexpr uint32_t id_dkv = make_idesc(fmt, fmt, 0, 1, 256, kD);   // dV, dK   : A in TMEM, B MN-major
@@ -264,99 +323,120 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
             mma_ts_pair(d_t, a_t + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), id_dkv, (acc || kk > 0) ? 1u : 0u);
         };
         const uint32_t lo_ds = lo_mn(sDS), lo_kt = lo_mn(sKt);
-        mbar_wait(bar(F_KV), 0, 500);
-        TSX(3);
-        mbar_wait(bar(F_QB), 0, 501);
-        TSX(4);
-        tc_fence_after();
-        mma_kmajor(tS, sK, sQb);
-        mma_commit_pair(bar(S_F));
-        mma_commit_pair(bar(E_QB));
-        mbar_wait(bar(F_DOB), 0, 502);
-        tc_fence_after();
-        mma_kmajor(tDP, sV, sDOb);
-        mma_commit_pair(bar(DP_F));
-        mma_commit_pair(bar(E_DOB));
         // TMEM regions and their tenants over one tile n (accumulators dV [256,384) and dK [384,512) aside):
         //   R1 = [0,128)   : S^T(n) fp32 -> once read: P^T(n) packed in [0,64), dQ(n-1 .. see below) in [64,128)
         //   R2 = [128,256) : dP^T(n) fp32 -> once read: dS^T(n) packed in [128,192)
         // Issue order dV(n), S^T(n+1), dK(n), dP^T(n+1), dQ(n): every MMA only waits for its own inputs; S^T(n+1) runs
         // while the compute warps still form dS^T(n), dP^T(n+1) right behind dK(n) while they form P^T(n+1), and dQ(n)
         // -- which has to wait for the exported half of dS^T -- lands in R1[64,128) after S^T(n+1) has been read, off the
-        // critical path (it only has to be drained before S^T(n+2) is issued).
-        for (int it = 0; it < n_iter; ++it) {
-          const uint32_t ph = it & 1;
-          const bool more = it + 1 < n_iter;
-          mbar_wait(bar(P_F), ph, 510);
-          TS(0);
-          mbar_wait(bar(S_RD), ph, 521);   // (already complete: every warp reads S^T before it delivers P^T; keeps the phases in step)
-          mbar_wait(bar(F_DOG), ph, 515);
+        // critical path (it only has to be drained before S^T(n+2) is issued).  Tiles are numbered `git` across ALL items of
+        // this pair (barrier phases continue); an item's first S^T / dP^T are issued while its predecessor's epilogue runs.
+        int git = 0, kitem = 0;
+        for (int r = 0; r < rounds; ++r) {
+          const int L = item_of_round(r);
+          Bwd2Work w;
+          if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+          const bool ts_on = FA_BWD2_TS && r == 0 && blockIdx.x < 2;
+          (void)ts_on;
+          mbar_wait(bar(F_KV), kitem & 1, 500);
+          if (r == 0) TSX(3);
+          // first tile of the item: S^T and dP^T (runs under the previous item's epilogue)
+          if (git > 0) mbar_wait(bar(DQ_E), (git & 1) ^ 1, 523);   // dQ(git-1) drained out of R1[64,128) in both CTAs
+          mbar_wait(bar(F_QB), git & 1, 501);
+          if (r == 0) TSX(4);
           tc_fence_after();
-          mma_ts_mn(tDV, tS, sDOg, it > 0);
-          mma_commit_pair(bar(E_DOG));
-#if FA_BWD2_TS
-          mma_commit_pair(bar(T_DV));
-#endif
-          TS(1);
-          if (more) {
-            if (it > 0) mbar_wait(bar(DQ_E), ph ^ 1, 513);   // dQ(it-1) drained out of R1[64,128) in both CTAs
-            TS(6);
-            mbar_wait(bar(F_QB), (it + 1) & 1, 512);
-            TS(2);
+          mma_kmajor(tS, sK, sQb);
+          mma_commit_pair(bar(S_F));
+          mma_commit_pair(bar(E_QB));
+          mbar_wait(bar(F_DOB), git & 1, 502);
+          tc_fence_after();
+          mma_kmajor(tDP, sV, sDOb);
+          mma_commit_pair(bar(DP_F));
+          mma_commit_pair(bar(E_DOB));
+          // dV / dK accumulators: the previous item's epilogue (both CTAs) must have read them out of TMEM
+          if (kitem > 0) mbar_wait(bar(ACC_FREE), (kitem - 1) & 1, 524);
+          for (int it = 0; it < w.n_iter; ++it, ++git) {
+            const uint32_t ph = git & 1;
+            const bool more = it + 1 < w.n_iter;
+            mbar_wait(bar(P_F), ph, 510);
+            TS(0);
+            mbar_wait(bar(S_RD), ph, 521);   // (already complete: every warp reads S^T before it delivers P^T; keeps the phases in step)
+            mbar_wait(bar(F_DOG), ph, 515);
             tc_fence_after();
-            mma_kmajor(tS, sK, sQb);
-            mma_commit_pair(bar(S_F));
-            mma_commit_pair(bar(E_QB));
+            mma_ts_mn(tDV, tS, sDOg, it > 0);
+            mma_commit_pair(bar(E_DOG));
 #if FA_BWD2_TS
-            mma_commit_pair(bar(T_S));
+            mma_commit_pair(bar(T_DV));
 #endif
-          }
-          mbar_wait(bar(DS_F), ph, 511);
-          TS(3);
-          mbar_wait(bar(F_QG), ph, 516);
-          tc_fence_after();
-          mma_ts_mn(tDK, tDP, sQg, it > 0);
-          mma_commit_pair(bar(E_QG));
+            TS(1);
+            if (more) {
+              if (git > 0) mbar_wait(bar(DQ_E), ph ^ 1, 513);   // dQ(git-1) drained out of R1[64,128) in both CTAs
+              TS(6);
+              mbar_wait(bar(F_QB), (git + 1) & 1, 512);
+              TS(2);
+              tc_fence_after();
+              mma_kmajor(tS, sK, sQb);
+              mma_commit_pair(bar(S_F));
+              mma_commit_pair(bar(E_QB));
 #if FA_BWD2_TS
-          mma_commit_pair(bar(T_DK));
+              mma_commit_pair(bar(T_S));
 #endif
-          if (more) {
-            mbar_wait(bar(F_DOB), (it + 1) & 1, 514);
+            }
+            mbar_wait(bar(DS_F), ph, 511);
+            TS(3);
+            mbar_wait(bar(F_QG), ph, 516);
             tc_fence_after();
-            mma_kmajor(tDP, sV, sDOb);
-            mma_commit_pair(bar(DP_F));
-            mma_commit_pair(bar(E_DOB));
+            mma_ts_mn(tDK, tDP, sQg, it > 0);
+            mma_commit_pair(bar(E_QG));
 #if FA_BWD2_TS
-            mma_commit_pair(bar(T_DP));
+            mma_commit_pair(bar(T_DK));
 #endif
-            TS(7);
-          }
-          mbar_wait(bar(DS_IN), ph, 517);     // dS^T rows of both key blocks have landed in my shared memory ...
-          TS(4);
-          mbar_wait(bar(DS_PEER), ph, 518);   // ... and in the peer's
-          TS(5);
-          if (more) mbar_wait(bar(S_RD), (it + 1) & 1, 519);   // S^T(it+1) is out of R1: its upper half is free for dQ
-          else if (it > 0) mbar_wait(bar(DQ_E), ph ^ 1, 522);  // last tile: no S^T issue waited for the previous dQ's drain
-          fence_proxy_async();
-          tc_fence_after();
+            if (more) {
+              mbar_wait(bar(F_DOB), (git + 1) & 1, 514);
+              tc_fence_after();
+              mma_kmajor(tDP, sV, sDOb);
+              mma_commit_pair(bar(DP_F));
+              mma_commit_pair(bar(E_DOB));
+#if FA_BWD2_TS
+              mma_commit_pair(bar(T_DP));
+#endif
+              TS(7);
+            }
+            if (it == 0) mbar_wait(bar(F_KT), kitem & 1, 525);   // this item's K^T panels (both CTAs)
+            mbar_wait(bar(DS_IN), ph, 517);     // dS^T rows of both key blocks have landed in my shared memory ...
+            TS(4);
+            mbar_wait(bar(DS_PEER), ph, 518);   // ... and in the peer's
+            TS(5);
+            if (more) mbar_wait(bar(S_RD), (git + 1) & 1, 519);   // S^T(git+1) is out of R1: its upper half is free for dQ
+            else if (git > 0) mbar_wait(bar(DQ_E), ph ^ 1, 522);  // last tile of the item: no S^T issue waited for the previous dQ's drain
+            fence_proxy_async();
+            tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk)
-            mma_ss_pair(tS + 64, mk(hi_mn, lo_ds + kk * (2048 >> 4)), mk(hi_mn, lo_kt + kk * (2048 >> 4)), id_dq, kk > 0);
-          mma_commit_pair(bar(DQ_F));
+            for (int kk = 0; kk < 16; ++kk)
+              mma_ss_pair(tS + 64, mk(hi_mn, lo_ds + kk * (2048 >> 4)), mk(hi_mn, lo_kt + kk * (2048 >> 4)), id_dq, kk > 0);
+            mma_commit_pair(bar(DQ_F));
 #if FA_BWD2_TS
-          mma_commit_pair(bar(T_DQ));
+            mma_commit_pair(bar(T_DQ));
 #endif
+          }
+          mma_commit_pair(bar(DKV_F));
+          ++kitem;
+          if (r == 0) TSX(5);
         }
-        mma_commit_pair(bar(DKV_F));
-        TSX(5);
       }
       if (rank == 1 && elect_one()) {
-        // relay: tell the leader when this CTA's dS^T tile (local stores + the peer's st.async) is complete
+        // relay: tell the leader when this CTA's dS^T tile (local stores + the peer's bulk copy) is complete
         const uint32_t peer_bar = mapa_rank(bar(DS_PEER), 0);
-        for (int it = 0; it < n_iter; ++it) {
-          mbar_wait(bar(DS_IN), it & 1, 520);
-          fence_proxy_async();
-          mbar_arrive_cluster(peer_bar);
+        int git = 0;
+        for (int r = 0; r < rounds; ++r) {
+          const int L = item_of_round(r);
+          Bwd2Work w;
+          if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+          for (int it = 0; it < w.n_iter; ++it, ++git) {
+            mbar_wait(bar(DS_IN), git & 1, 520);
+            fence_proxy_async();
+            mbar_arrive_cluster(peer_bar);
+          }
         }
       }
       __syncwarp();
@@ -371,11 +451,19 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     const uint32_t t_dq = tS + 64 + (uint32_t(wq * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
     const uint32_t dqe = mapa_rank(bar(DQ_E), 0);
+    int git = 0;
+    for (int r = 0; r < rounds; ++r) {
+    const int L = item_of_round(r);
+    Bwd2Work w;
+    if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+    const bool ts_on = FA_BWD2_TS && r == 0 && blockIdx.x < 2;
+    (void)ts_on;
+    const int bidb = w.bidb, pair = w.pair, shift = w.shift;
     const WsRows ws = ws_rows(p.cu_seqlens_q, bidb, p.h, 0, p.sq_r, p.ws_head_pitch);   // tensor-map coordinates only
-    for (int it = 0; it < n_iter; ++it) {
-      const int hq = hk * p.g + it / n_m;
-      const int m = m_min + it % n_m;
-      mbar_wait(bar(DQ_F), it & 1, 600);
+    for (int it = 0; it < w.n_iter; ++it, ++git) {
+      const int hq = w.hk * p.g + it / w.n_m;
+      const int m = w.m_min + it % w.n_m;
+      mbar_wait(bar(DQ_F), git & 1, 600);
       if (warp == 8 && lane == 0) TS(12);
       tc_fence_after();
       // deterministic mode: the pairs that touch (query block m, query half rank) add in ascending pair order
@@ -406,7 +494,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       if (warp == 8 && lane == 0) TS(13);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {   // two rounds: 32-column chunk c of each d half
-        if (leader && (it > 0 || c > 0)) tma_store_wait_read<0>();   // the previous reduce-adds have read the staging
+        if (leader && (git > 0 || c > 0)) tma_store_wait_read<0>();   // the previous reduce-adds have read the staging
         named_bar_sync(1, 128);
         uint8_t* dst = smem_gen + Cfg::kSDQ + dh * 8192 + q * 128;
 #pragma unroll
@@ -428,22 +516,19 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sem), "r"(my_turn + 1) : "memory");
       }
     }
+    }
     if (leader) tma_store_wait_read<0>();   // the staging buffers must outlive the reads; completion is the grid's business
   } else {
     // ================================================================ compute warps (as in fa_bwd_kernel)
     reg_alloc<Cfg::kRegsCompute>();
     const int wq = warp & 3, hf = warp >> 2;          // key-row quadrant, query half
     const int r = wq * 32 + lane;                       // key row within this CTA's block
-    const int j = key0 + r;                             // key index in the sequence
     const uint32_t lane_sel = uint32_t(wq * 32) << 16;
     const uint32_t t_s = tS + lane_sel + hf * 64;
     const uint32_t t_dp = tDP + lane_sel + hf * 64;
     const uint32_t t_p = tS + lane_sel + hf * 32;
     const uint32_t t_ds = tDP + lane_sel + hf * 32;   // dS^T packed: over the dP^T columns [0,64) once both halves are read
     const float scale_log2 = p.scale_log2;
-    const int i_lo = p.has_right ? j - shift - p.wr : -(1 << 30);
-    const int i_hi = p.has_left ? j - shift + p.wl : (1 << 30);
-    const bool key_valid = j < sk_b;
     const uint32_t pf = mapa_rank(bar(P_F), 0), dsf = mapa_rank(bar(DS_F), 0), srd = mapa_rank(bar(S_RD), 0);
     // my dS^T row (key 128*rank + r of the pair, 64 queries of half hf) lives in the CTA that owns query half hf
     // exporter warps stage their 32 rows (4 KB) locally and ship them with one bulk copy into the peer's sDS
@@ -458,15 +543,30 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         drop.off_lo = uint32_t(of); drop.off_hi = uint32_t(of >> 32);
       }
     }
-    for (int it = 0; it < n_iter; ++it) {
+    const uint32_t acc_free = mapa_rank(bar(ACC_FREE), 0);
+    int git = 0, kitem = 0;
+    for (int rr = 0; rr < rounds; ++rr) {
+    const int L = item_of_round(rr);
+    Bwd2Work w;
+    if (L >= total_items || !bwd2_decode_work(p, L, w)) continue;
+    const bool ts_on = FA_BWD2_TS && rr == 0 && blockIdx.x < 2;
+    (void)ts_on;
+    const int n_iter = w.n_iter, n_m = w.n_m, m_min = w.m_min, hk = w.hk, bidb = w.bidb, shift = w.shift, sk_b = w.sk_b;
+    const int k_off = w.k_off;
+    const int key0 = w.pkey0 + 128 * int(rank);
+    const int j = key0 + r;                             // key index in the sequence
+    const int i_lo = p.has_right ? j - shift - p.wr : -(1 << 30);
+    const int i_hi = p.has_left ? j - shift + p.wl : (1 << 30);
+    const bool key_valid = j < sk_b;
+    for (int it = 0; it < n_iter; ++it, ++git) {
       const int hq = hk * p.g + it / n_m;
       const int m = m_min + it % n_m;
-      const int st = it & 1;
+      const int st = git & 1;
       const int q0 = m * 128 + hf * 64;
       float slope = 0.f;
       if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + hq] / p.scale_eff;
-      mbar_wait(bar(F_ST0 + st), (it >> 1) & 1, 700);
-      mbar_wait(bar(S_F), it & 1, 701);
+      mbar_wait(bar(F_ST0 + st), (git >> 1) & 1, 700);
+      mbar_wait(bar(S_F), git & 1, 701);
       if (warp == 0 && lane == 0) TS(8);
       tc_fence_after();
       uint32_t su[64];
@@ -538,7 +638,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         if (lane == 0) mbar_arrive_cluster(pf);
         if (warp == 0 && lane == 0) TS(9);
       }
-      mbar_wait(bar(DP_F), it & 1, 702);
+      mbar_wait(bar(DP_F), git & 1, 702);
       if (warp == 0 && lane == 0) TS(10);
       tc_fence_after();
       uint32_t dk_[32];
@@ -591,7 +691,9 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       // written into the CTA that owns query half hf (the peer through distributed shared memory)
       // dQ of the previous tile (issued BEHIND this tile's dP^T) must have finished reading sDS in both CTAs before
       // anyone overwrites it (locally or with a bulk copy into the peer)
-      if (it > 0) mbar_wait(bar(DQ_F), (it - 1) & 1, 703);
+      if (git > 0) mbar_wait(bar(DQ_F), (git - 1) & 1, 703);
+      // first tile of an item: sDS also staged the previous item's dV for its TMA stores (in both CTAs)
+      if (it == 0 && kitem > 0) mbar_wait(bar(STAGE_FREE), (kitem - 1) & 1, 704);
       {
         uint8_t* dst = ds_is_local ? smem_gen + Cfg::kSDS + (128 * int(rank) + r) * 128 : smem_gen + Cfg::kSDX + r * 128;
 #pragma unroll
@@ -621,13 +723,14 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     }
     // ---------------------------------------------------------------- epilogue: dK (x scale), dV (x 1/p_keep)
     if (n_iter > 0) {
-      mbar_wait(bar(DKV_F), 0, 710);
-      if (threadIdx.x == 0) TSX(6);
+      mbar_wait(bar(DKV_F), kitem & 1, 710);
+      if (threadIdx.x == 0 && rr == 0) TSX(6);
       tc_fence_after();
     }
     const int bk = p.cu_seqlens_k ? 0 : bidb;
-    // Fast path: the 128 x 128 dV / dK tiles go through the (now idle) V / K shared-memory tiles and leave with TMA
-    // stores (rows / columns beyond the tensor are clipped by the tensor map).  A ragged tail block of a PACKED varlen
+    // Fast path: the 128 x 128 dV / dK tiles go through the (now idle) dS^T / K^T shared-memory tiles and leave with TMA
+    // stores (rows / columns beyond the tensor are clipped by the tensor map); K / V themselves are already being
+    // reloaded for the next item.  A ragged tail block of a PACKED varlen
     // batch borders the next sequence's rows, so it takes the predicated per-thread path, as does an empty work item.
     const bool tma_epilogue = n_iter > 0 && !(p.cu_seqlens_k && key0 + 128 > sk_b);
     if (tma_epilogue) {
@@ -635,11 +738,16 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       for (int which = 0; which < 2; ++which) {
         const uint32_t t_src = (which == 0 ? tDV : tDK) + lane_sel + hf * 64;
         const float mul = which == 0 ? (kDropout ? drop.rp : 1.0f) : p.scale;
-        uint8_t* dst = smem_gen + (which == 0 ? Cfg::kSV : Cfg::kSK) + hf * 16384 + r * 128;   // panel hf = d columns [64 hf, 64 hf + 64)
+        uint8_t* dst = smem_gen + (which == 0 ? Cfg::kSDS : Cfg::kSKt) + hf * 16384 + r * 128;   // panel hf = d columns [64 hf, 64 hf + 64)
         uint32_t o[64];
         tmem_ld_x32(t_src, o);
         tmem_ld_x32(t_src + 32, o + 32);
         tmem_wait_ld();
+        if (which == 1) {   // both accumulators are in registers: the next item's dV / dK MMAs may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_free);
+        }
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
           uint4 v4;
@@ -655,11 +763,13 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       if (threadIdx.x == 0) {
 #pragma unroll
         for (int pn = 0; pn < 2; ++pn) {
-          tma_store_4d(&p.tm_dv, sV + pn * 16384, pn * 64, k_off + key0, hk, bk);
-          tma_store_4d(&p.tm_dk, sK + pn * 16384, pn * 64, k_off + key0, hk, bk);
+          tma_store_4d(&p.tm_dv, sDS + pn * 16384, pn * 64, k_off + key0, hk, bk);
+          tma_store_4d(&p.tm_dk, sKt + pn * 16384, pn * 64, k_off + key0, hk, bk);
         }
         tma_store_commit();
         tma_store_wait_read<0>();   // shared memory must outlive the reads; the writes complete on their own
+        mbar_arrive(bar(STAGE_FREE));                                      // my staging is free again: tell myself ...
+        mbar_arrive_cluster(mapa_rank(bar(STAGE_FREE), rank ^ 1u));        // ... and the peer (it bulk-copies into my sDS)
       }
     } else {
 #pragma unroll
@@ -677,6 +787,11 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         if (n_iter > 0) {
           tmem_ld_x32(t_src + hf * kHalf + cc, o);
           tmem_wait_ld();
+          if (which == 1 && cc + 32 >= kHalf) {   // last TMEM read of this warp: the accumulators may be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_free);
+          }
         }
         if (key_valid) {
 #pragma unroll
@@ -696,7 +811,13 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         }
       }
     }
+    if (n_iter > 0 && threadIdx.x == 0) {   // no staging used on this path: free at once (both CTAs always arrive, see above)
+      mbar_arrive(bar(STAGE_FREE));
+      mbar_arrive_cluster(mapa_rank(bar(STAGE_FREE), rank ^ 1u));
     }
+    }
+    if (n_iter > 0) ++kitem;
+    }   // work items
   }
 
   if (threadIdx.x == 0) TSX(7);

@@ -84,17 +84,18 @@ static int launch_bwd_main(const BwdKernelParams& kp, dim3 grid, cudaStream_t st
 
 // CTA-pair main loop (fa_bwd2_sm100.cuh): head dim 128 only
 template <typename T, bool kSoftcap, bool kDropout>
-static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+static int launch_bwd_pair(const BwdKernelParams& kp, dim3 grid, cudaStream_t stream, int sm_margin) {
   static PerDeviceOnce configured;
   auto kern = fa_bwd2_kernel<T, kSoftcap, kDropout>;
   if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Cfg::kSmemBytes); });
       e != cudaSuccess)
     return set_error(std::string("cudaFuncSetAttribute(bwd2): ") + cudaGetErrorString(e));
-  grid.x = (grid.x + 1) / 2 * 2;  // whole pairs (compile-time cluster dims (2,1,1))
-  if (kp.sched_lpt) {
-    const unsigned pairs = grid.x / 2, c = unsigned(kp.sched_lpt);
-    grid = dim3(2 * c, grid.y * grid.z, (pairs + c - 1) / c);
-  }
+  // persistent: one CTA pair (cluster) per two SMs, fewer if there is less work; `sm_margin` SMs left free
+  (void)grid;
+  int sms = num_sms() - std::max(0, sm_margin);
+  if (sms < 2) sms = 2;
+  const int clusters = int(std::min<int64_t>(sms / 2, kp.total_items));
+  grid = dim3(unsigned(2 * std::max(clusters, 1)), 1, 1);
   kern<<<grid, Bwd2Cfg::kThreads, Bwd2Cfg::kSmemBytes, stream>>>(kp);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
@@ -224,9 +225,20 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
   }
   if constexpr (kD == 128) {
     if (pair) {
-      rc = a.p_dropout > 0.f ? launch_bwd_pair<T, false, true>(kp, grid, stream)
-         : a.softcap > 0.f ? launch_bwd_pair<T, true, false>(kp, grid, stream)
-                           : launch_bwd_pair<T, false, false>(kp, grid, stream);
+      // work items of the persistent pair kernel: (pair of key blocks, kv head, batch); groups of (kv head, batch)
+      // combinations whose Q + dO + dq_accum stream (16 bytes per query x head-dim element and query head) shares L2
+      kp.num_pairs = (a.seqlen_k + 255) / 256;
+      const int64_t hz_total = int64_t(a.h_k) * a.b;
+      const double q_bytes = double(a.seqlen_q) * a.d * (2 + 2 + 4) * (a.h / a.h_k);
+      int64_t grp = int64_t(std::max(1.0, std::floor(48.0 * 1024 * 1024 / std::max(q_bytes, 1.0))));
+      if (const char* e = getenv("FA_B200_SCHED_GROUP_BWD")) grp = atoi(e);
+      kp.sched_group = int(std::max<int64_t>(1, std::min<int64_t>(grp, hz_total)));
+      const int64_t total = int64_t(kp.num_pairs) * hz_total;
+      if (total > INT32_MAX) return set_error("too many work items");
+      kp.total_items = int(total);
+      rc = a.p_dropout > 0.f ? launch_bwd_pair<T, false, true>(kp, grid, stream, a.sm_margin)
+         : a.softcap > 0.f ? launch_bwd_pair<T, true, false>(kp, grid, stream, a.sm_margin)
+                           : launch_bwd_pair<T, false, false>(kp, grid, stream, a.sm_margin);
       launched = true;
     }
   }

@@ -57,7 +57,8 @@ struct BwdKernelParams {
   float scale_eff;           // scale of the logits inside exp: softcap if softcap > 0 else softmax_scale
   float scale_log2;          // scale_eff * log2(e)
   float softcap_pre;
-  int sched_lpt;              // key block (pair) index is the slowest grid dimension: heavy (masked) work first
+  int sched_lpt;              // (single-CTA kernel) key block index is the slowest grid dimension: heavy (masked) work first
+  int num_pairs, sched_group, total_items;   // persistent CTA-pair kernel (fa_bwd2_sm100.cuh): work-item enumeration
   DropoutParams drop;         // kDropout kernels only: the forward's rng_state and p_dropout
   const uint64_t* rng_state;  // device copy of {seed, offset}; overrides drop.seed/off when non-null
   float* dq_accum;            // fa_bwd256_kernel only (adds its dQ partials with red.global instead of TMA): (b, h, sq_r, 256)

@@ -1,8 +1,14 @@
 // fa_fwd_sm100.cuh — forward attention mainloop for sm_100a (B200).
 //
-// One CTA owns up to two 128-row query tiles ("tile 0/1", 256 packed rows) of one (batch, head-slot,
-// split) and streams the K/V blocks of that work item right-to-left (masked blocks first, like the
-// reference: csrc/flash_attn/src/flash_fwd_kernel.h:138-140,274).
+// PERSISTENT: the grid is one CTA per SM (two for the 1-tile configuration); every CTA loops over work items.  A work
+// item is up to two 128-row query tiles ("tile 0/1", 256 packed rows) of one (batch, head-slot, split); its K/V blocks
+// stream right-to-left (masked blocks first, like the reference: csrc/flash_attn/src/flash_fwd_kernel.h:138-140,274).
+// Item order (fwd_decode_work): heavy (causal) m-blocks first inside groups of heads whose K/V fit L2 together, dealt to
+// the CTAs in snake order (round r: CTA c takes item r*G + c, or r*G + G-1-c on odd rounds) so that every CTA pairs a heavy
+// with a light item (cf. the reference's LPT + L2 swizzle scheduler, flash_attn/cute/tile_scheduler.py:458-530); packed
+// varlen batches are enumerated through a per-batch m-block prefix sum written by fa_fwd_varlen_prepare (cf.
+// hopper/flash_prepare_scheduler.cu:43-215) instead of a max_seqlen grid with early exits.  Barrier phases, the K/V ring
+// and TMEM stay live across items: the next item's Q / K loads and first S = QK^T run under the current item's epilogue.
 //
 //   warp 0-3  softmax warpgroup for tile 0 : tcgen05.ld S row -> mask -> online max/sum -> exp2 ->
 //   warp 4-7  softmax warpgroup for tile 1   tcgen05.st P (aliases S in TMEM) ; lazy O rescale ; epilogue
@@ -23,6 +29,10 @@
 
 #include "fa_dropout.cuh"
 #include "fa_ptx.cuh"
+
+#ifndef FA_FWD_REGS_SOFTMAX2
+#define FA_FWD_REGS_SOFTMAX2 208   // setmaxnreg of the two softmax warpgroups (2-tile configuration); the rest gets 504 - 2x
+#endif
 
 namespace fa {
 
@@ -59,8 +69,10 @@ struct FwdKernelParams {
   int has_right, has_left;  // window limits active (causal => has_right, wr = 0)
   int wl, wr;
   int reverse_m;            // schedule heavy m-blocks first (causal)
-  int sched_lpt;            // 0: head-major grid; c > 0: chunked work-major grid (see the work-item prologue)
-  int num_m_blocks;
+  int sched_group;          // (head-slot x batch x split) combinations per scheduling group: their K/V share L2
+  int num_m_blocks;         // dense: m-blocks per (batch, head slot); varlen: upper bound (max_seqlen_q)
+  int total_items;          // dense: num_m_blocks * head slots * batch * splits; varlen: read from varlen_prefix[b]
+  const int* varlen_prefix; // packed varlen: exclusive prefix sum of per-batch m-block counts, (b + 1) ints, else nullptr
   float scale;              // effective softmax scale (softcap if softcap > 0)
   float scale_log2;         // scale * log2(e)
   float softcap_pre;        // softmax_scale / softcap, 0 = off
@@ -82,8 +94,8 @@ struct FwdCfg {
   static constexpr int kWarpMma = 4 * kTiles, kWarpTma = 4 * kTiles + 1, kWarpClean = 4 * kTiles + 2;
   // setmaxnreg split: the CTA's register pool is kThreads * 168 (launch bounds 384 x 1 -> 168 regs/thread);
   // 2 softmax warpgroups + 1 MMA/TMA warpgroup must not ask for more than that or setmaxnreg.inc blocks forever.
-  static constexpr int kRegsSoftmax = kTiles == 2 ? 216 : 200;
-  static constexpr int kRegsOther = kTiles == 2 ? 72 : 56;
+  static constexpr int kRegsSoftmax = kTiles == 2 ? FA_FWD_REGS_SOFTMAX2 : 200;
+  static constexpr int kRegsOther = kTiles == 2 ? (504 - 2 * FA_FWD_REGS_SOFTMAX2) : 56;
   static_assert(kTiles * kRegsSoftmax + kRegsOther <= (kTiles + 1) * (kTiles == 2 ? 168 : 128),
                 "setmaxnreg split exceeds the CTA register pool");
   static constexpr int kPanels = kD * kBytes / 128;        // 128-byte swizzle panels per row (64 x 16-bit or 128 x 8-bit)
@@ -92,7 +104,7 @@ struct FwdCfg {
   static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
   static constexpr int kSmemQ = kTiles * kTileBytes;
   static constexpr int kSmemKV = kStages * kTileBytes;
-  static constexpr int kNumBars = 2 + 2 * kStages + 9;
+  static constexpr int kNumBars = 2 + 2 * kStages + 13;   // + q_empty[2], o_free[2] of the persistent loop
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");  // hd256 (1 tile, 194 KB) runs one CTA per SM
 };
@@ -152,6 +164,140 @@ __device__ unsigned long long g_fwd_ts[16 * 16];   // [iteration - 8][event]
 #define FA_FWD_POLY_PAIRS 1  // measured on B200 (r01): 0 -> 1315, 1 -> 1339, 2 -> 1307, 3 -> 1147, 4 -> 1046 TFLOP/s fwd
 #endif
 
+// ---------------------------------------------------------------------------------------------- work items
+struct FwdWork {
+  int m_block, slot, bidb, split;
+  int q_off, sq_b, k_off, sk_b, rows_total, row0, ntiles;
+  int hk_idx, shift, nblk_total;
+  int n_min, n_max, nblocks;   // the CTA's K/V block stream: j = n_max - 1 ... n_min  (iteration it <-> block n_max-1-it)
+  int it_lo0, it_hi0, it_lo1, it_hi1;   // tile i takes part in stream iterations [it_lo_i, it_hi_i) (a causal / local
+                               // mask can spare the lower-row tile's first block or the upper-row tile's last one)
+  __device__ __forceinline__ int it_lo(int i) const { return i == 0 ? it_lo0 : it_lo1; }
+  __device__ __forceinline__ int it_hi(int i) const { return i == 0 ? it_hi0 : it_hi1; }
+  int v_tail;                  // the first streamed block is the ragged last block of the sequence
+};
+
+// Linear item index -> work item.  Returns false for an index that holds no work (past the end / empty m-block).
+template <int kRowsPerCta, int kTiles>
+__device__ __forceinline__ bool fwd_decode_work(const FwdKernelParams& p, int L, FwdWork& w) {
+  const int nslots = p.h / p.gp;
+  int m_idx, nm;
+  if (p.varlen_prefix) {   // batch-major; inside a batch heavy m-blocks first, head slots fastest
+    int lo = 0, hi = p.b;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.varlen_prefix[mid] * nslots <= L) lo = mid; else hi = mid;
+    }
+    w.bidb = lo;
+    const int rem = L - p.varlen_prefix[lo] * nslots;
+    nm = p.varlen_prefix[lo + 1] - p.varlen_prefix[lo];
+    m_idx = rem / nslots;
+    w.slot = rem - m_idx * nslots;
+    w.split = 0;
+  } else {
+    const int hz_total = nslots * p.b * p.num_splits;
+    const int per_group = p.num_m_blocks * p.sched_group;
+    const int grp = L / per_group;
+    const int within = L - grp * per_group;
+    int gsz = hz_total - grp * p.sched_group;
+    gsz = gsz < p.sched_group ? gsz : p.sched_group;
+    m_idx = within / gsz;
+    const int hz = grp * p.sched_group + (within - m_idx * gsz);
+    nm = p.num_m_blocks;
+    w.slot = hz % nslots;
+    const int bz = hz / nslots;
+    w.bidb = bz / p.num_splits;
+    w.split = bz - w.bidb * p.num_splits;
+  }
+  w.m_block = p.reverse_m ? (nm - 1 - m_idx) : m_idx;
+  const int bidb = w.bidb;
+  w.q_off = 0; w.sq_b = p.sq; w.k_off = 0; w.sk_b = p.sk;
+  if (p.cu_seqlens_q) { w.q_off = p.cu_seqlens_q[bidb]; w.sq_b = p.cu_seqlens_q[bidb + 1] - w.q_off; }
+  if (p.cu_seqlens_k) { w.k_off = p.cu_seqlens_k[bidb]; w.sk_b = p.cu_seqlens_k[bidb + 1] - w.k_off; }
+  if (p.seqused_k) w.sk_b = p.seqused_k[bidb];
+  if (p.seqused_q) w.sq_b = p.seqused_q[bidb];
+  if (p.leftpad_k) {  // keys start leftpad_k rows into the batch's rows; seqlen_k = seqused_k - leftpad_k (block_info.h:12-45)
+    const int lp = p.leftpad_k[bidb];
+    w.k_off += lp;
+    w.sk_b -= lp;
+  }
+  w.rows_total = w.sq_b * p.gp;
+  w.row0 = w.m_block * kRowsPerCta;
+  if (w.row0 >= w.rows_total) return false;
+  w.ntiles = (kTiles == 2 && w.row0 + 128 < w.rows_total) ? 2 : 1;
+  w.hk_idx = (w.slot * p.gp) / p.g;
+  w.shift = w.sk_b - w.sq_b;  // bottom-right alignment (mask.h:172-173)
+  w.nblk_total = ceil_div(w.sk_b, 128);
+  int s_lo = 0, s_hi = w.nblk_total;
+  if (p.num_splits > 1) {  // equal block ranges per split (flash_fwd_kernel.h:535-543)
+    const int per = ceil_div(w.nblk_total, p.num_splits);
+    s_lo = w.split * per;
+    s_hi = (w.split + 1) * per;
+  }
+  int t_min0 = 0, t_max0 = 0, t_min1 = 0, t_max1 = 0;
+  w.n_min = 1 << 30; w.n_max = 0;
+#pragma unroll
+  for (int i = 0; i < kTiles; ++i) {
+    if (i < w.ntiles) {
+      const int r_lo = w.row0 + i * 128;
+      const int r_hi = r_lo + 127 < w.rows_total - 1 ? r_lo + 127 : w.rows_total - 1;
+      int nmax = w.nblk_total, nmin = 0;
+      if (p.has_right) {
+        const int lim = r_hi / p.gp + 1 + w.shift + p.wr;  // exclusive column limit of the tile's last row
+        const int nb = lim <= 0 ? 0 : ceil_div(lim, 128);
+        nmax = nb < nmax ? nb : nmax;
+      }
+      if (p.has_left) {
+        const int lo = r_lo / p.gp + w.shift - p.wl;
+        nmin = lo <= 0 ? 0 : lo / 128;
+      }
+      nmin = nmin > s_lo ? nmin : s_lo;
+      nmax = nmax < s_hi ? nmax : s_hi;
+      if (nmax > nmin) {
+        if (i == 0) { t_min0 = nmin; t_max0 = nmax; } else { t_min1 = nmin; t_max1 = nmax; }
+        w.n_min = nmin < w.n_min ? nmin : w.n_min;
+        w.n_max = nmax > w.n_max ? nmax : w.n_max;
+      }
+    }
+  }
+  w.nblocks = w.n_max > w.n_min ? w.n_max - w.n_min : 0;
+  w.it_lo0 = w.it_hi0 = w.it_lo1 = w.it_hi1 = 0;
+  if (t_max0 > t_min0) { w.it_lo0 = w.n_max - t_max0; w.it_hi0 = w.n_max - t_min0; }
+  if (kTiles == 2 && t_max1 > t_min1) { w.it_lo1 = w.n_max - t_max1; w.it_hi1 = w.n_max - t_min1; }
+  w.v_tail = (w.nblocks > 0 && w.n_max == w.nblk_total && (w.sk_b & 127)) ? 1 : 0;
+  return true;
+}
+
+// per-batch m-block counts of a packed varlen batch -> exclusive prefix sum (b + 1 ints): the persistent kernel
+// enumerates exactly the m-blocks that exist (reference: hopper/flash_prepare_scheduler.cu:43-215)
+static __global__ void __launch_bounds__(256) fa_fwd_varlen_prepare(const int* __restrict__ cu_seqlens_q, const int* __restrict__ seqused_q,
+                                                            int b, int gp, int rows_per_cta, int* __restrict__ prefix) {
+  __shared__ int part[256];
+  const int t = threadIdx.x;
+  const int per = (b + 255) / 256;
+  int sum = 0;
+  for (int i = t * per; i < b && i < (t + 1) * per; ++i) {
+    int sq = cu_seqlens_q[i + 1] - cu_seqlens_q[i];
+    if (seqused_q) sq = seqused_q[i];
+    sum += (sq * gp + rows_per_cta - 1) / rows_per_cta;
+  }
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    int acc = 0;
+    for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = acc; acc += v; }
+  }
+  __syncthreads();
+  int acc = part[t];
+  for (int i = t * per; i < b && i < (t + 1) * per; ++i) {
+    int sq = cu_seqlens_q[i + 1] - cu_seqlens_q[i];
+    if (seqused_q) sq = seqused_q[i];
+    prefix[i] = acc;
+    acc += (sq * gp + rows_per_cta - 1) / rows_per_cta;
+    if (i == b - 1) prefix[b] = acc;
+  }
+}
+
 template <typename T, int kD, int kTiles, bool kDropout = false>
 __global__ void __launch_bounds__((FwdCfg<kD, 2, kTiles>::kThreads), (FwdCfg<kD, 2, kTiles>::kCtasPerSm))
 fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
@@ -162,67 +308,14 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   constexpr int kRowsPerCta = 128 * kTiles;
   constexpr int S = Cfg::kStages;
   constexpr float kNegInf = -INFINITY;
-  // of every 4 element pairs, how many use the FMA-pipe exp2 (fp8 has its own setting: its P is quantised to e4m3)
-  constexpr int kPolyPairs = kFp8 ? FA_FWD_POLY_PAIRS_FP8 : FA_FWD_POLY_PAIRS;
   constexpr int kPolyDeg = kFp8 ? FA_FWD_POLY_DEG_FP8 : 3;
+  constexpr int kPolyPairs = kFp8 ? FA_FWD_POLY_PAIRS_FP8 : FA_FWD_POLY_PAIRS;
 
-  // ------------------------------------------------------------------ work item
-  // default grid (m blocks, head slots, batch x splits).  sched_lpt = c > 0: grid (c, head slots x batch x splits,
-  // ceil(m blocks / c)) -- chunks of c adjacent m-blocks of one head stay together (they share K/V through L2) and the
-  // chunk index is the slowest dimension, so with a causal mask every head's heavy chunks are dispatched first
-  const int num_m_blocks = p.num_m_blocks;
-  const int m_idx = p.sched_lpt ? int(blockIdx.z) * p.sched_lpt + int(blockIdx.x) : int(blockIdx.x);
-  if (m_idx >= num_m_blocks) return;
-  const int m_block = p.reverse_m ? (num_m_blocks - 1 - m_idx) : m_idx;
-  const int nslots = p.h / p.gp;
-  const int slot = p.sched_lpt ? int(blockIdx.y) % nslots : int(blockIdx.y);   // index over h / gp
-  const int bz = p.sched_lpt ? int(blockIdx.y) / nslots : int(blockIdx.z);
-  const int bidb = bz / p.num_splits;
-  const int split = bz - bidb * p.num_splits;
-
-  int q_off = 0, sq_b = p.sq, k_off = 0, sk_b = p.sk;
-  if (p.cu_seqlens_q) { q_off = p.cu_seqlens_q[bidb]; sq_b = p.cu_seqlens_q[bidb + 1] - q_off; }
-  if (p.cu_seqlens_k) { k_off = p.cu_seqlens_k[bidb]; sk_b = p.cu_seqlens_k[bidb + 1] - k_off; }
-  if (p.seqused_k) sk_b = p.seqused_k[bidb];
-  if (p.seqused_q) sq_b = p.seqused_q[bidb];
-  if (p.leftpad_k) {  // keys start leftpad_k rows into the batch's rows; seqlen_k = seqused_k - leftpad_k (block_info.h:12-45)
-    const int lp = p.leftpad_k[bidb];
-    k_off += lp;
-    sk_b -= lp;
-  }
-  const int rows_total = sq_b * p.gp;
-  const int row0 = m_block * kRowsPerCta;
-  if (row0 >= rows_total) return;  // uniform for the whole CTA, nothing allocated yet
-  const int ntiles = (kTiles == 2 && row0 + 128 < rows_total) ? 2 : 1;
-
-  const int hk_idx = (slot * p.gp) / p.g;
-  const int shift = sk_b - sq_b;  // bottom-right alignment (mask.h:172-173)
-  const int nblk_total = ceil_div(sk_b, 128);
-  int n_min = 0, n_max = nblk_total;
-  {
-    const int qpos_lo = row0 / p.gp;
-    int last_row = row0 + kRowsPerCta - 1 < rows_total - 1 ? row0 + kRowsPerCta - 1 : rows_total - 1;
-    const int qpos_hi = last_row / p.gp;
-    if (p.has_right) {
-      int lim = qpos_hi + 1 + shift + p.wr;  // exclusive column limit of the last row
-      int nb = lim <= 0 ? 0 : ceil_div(lim, 128);
-      n_max = nb < n_max ? nb : n_max;
-    }
-    if (p.has_left) {
-      int lo = qpos_lo + shift - p.wl;
-      int nb = lo <= 0 ? 0 : lo / 128;
-      n_min = nb;
-    }
-    if (p.num_splits > 1) {  // equal block ranges per split (flash_fwd_kernel.h:535-543)
-      const int per = ceil_div(nblk_total, p.num_splits);
-      int lo = split * per, hi = (split + 1) * per;
-      n_min = n_min > lo ? n_min : lo;
-      n_max = n_max < hi ? n_max : hi;
-    }
-  }
-  const int nblocks = n_max > n_min ? n_max - n_min : 0;
-  // the first streamed block is the ragged last block of the sequence
-  const bool v_tail = (n_max == nblk_total) && (sk_b & 127);
+  // ------------------------------------------------------------------ item enumeration (identical in every role)
+  const int G = int(gridDim.x), cta = int(blockIdx.x);
+  const int total_items = p.varlen_prefix ? p.varlen_prefix[p.b] * (p.h / p.gp) : p.total_items;
+  const int rounds = (total_items + G - 1) / G;
+  auto item_of_round = [&](int r) { return r * G + ((r & 1) ? (G - 1 - cta) : cta); };
 
   // ------------------------------------------------------------------ shared memory carve-up
   extern __shared__ uint8_t smem_raw[];
@@ -238,6 +331,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   // bar_p_full(i): keys [0,64) of P_i are in TMEM; bar_p_full(i) + 16: keys [64,128)
   auto bar_o_full = [&](int i) { return sBar + 8u * (8 + 2 * S + i); };
   const uint32_t bar_v_clean = sBar + 8u * (10 + 2 * S);
+  auto bar_q_empty = [&](int i) { return sBar + 8u * (11 + 2 * S + i); };   // every QK^T of the item has read Q_i
+  auto bar_o_free = [&](int i) { return sBar + 8u * (13 + 2 * S + i); };    // the item's epilogue has read O_i out of TMEM
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSmemQ + Cfg::kSmemKV + 8 * Cfg::kNumBars);
@@ -254,10 +349,12 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_q_full(i), 1);
+        mbar_init(bar_q_empty(i), 1);
         mbar_init(bar_s_full(i), 1);
         mbar_init(bar_p_full(i), 4);  // one arrive per softmax warp
         mbar_init(bar_p_full(i) + 16, 4);
         mbar_init(bar_o_full(i), 1);
+        mbar_init(bar_o_free(i), 4);
       }
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_kv_full(s), 1);
@@ -280,36 +377,47 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   reg_dealloc<Cfg::kRegsOther>();
   // ================================================================== TMA producer
   if (warp == Cfg::kWarpTma) {
-    if (nblocks > 0 && elect_one()) {
-      const int bq = p.cu_seqlens_q ? 0 : bidb;
-      for (int i = 0; i < ntiles; ++i) {
-        mbar_arrive_expect_tx(bar_q_full(i), Cfg::kTileBytes);
-        const int qpos0 = q_off + (row0 + i * 128) / p.gp;
+    if (elect_one()) {
+      int ring = 0;              // running K/V slot counter across items: K_it -> ring, V_it -> ring + 1
+      int q_items[2] = {0, 0};   // items so far that used Q tile i
+      for (int r = 0; r < rounds; ++r) {
+        const int L = item_of_round(r);
+        FwdWork w;
+        if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
+        const int bq = p.cu_seqlens_q ? 0 : w.bidb;
 #pragma unroll
-        for (int pn = 0; pn < Cfg::kPanels; ++pn)
-          tma_load_5d(sQ + i * Cfg::kTileBytes + pn * Cfg::kPanelBytes, &p.tm_q, bar_q_full(i), pn * Cfg::kPanelElems, 0, qpos0,
-                      slot, bq);
-      }
-      int ring = 0;  // running slot counter: K_it -> 2*it, V_it -> 2*it + 1
-      for (int it = 0; it < nblocks; ++it) {
-        const int j = n_max - 1 - it;
-        int row = k_off + j * 128, c3 = p.cu_seqlens_k ? 0 : (p.cache_batch_idx ? p.cache_batch_idx[bidb] : bidb);
-        if (p.page_size) {
-          const int pos = j * 128;
-          c3 = p.block_table[bidb * p.block_table_batch_stride + pos / p.page_size];
-          row = pos % p.page_size;
+        for (int i = 0; i < kTiles; ++i) {
+          if (w.it_hi(i) > w.it_lo(i)) {
+            if (q_items[i] > 0) mbar_wait(bar_q_empty(i), (q_items[i] - 1) & 1, 110 + i);
+            ++q_items[i];
+            mbar_arrive_expect_tx(bar_q_full(i), Cfg::kTileBytes);
+            const int qpos0 = w.q_off + (w.row0 + i * 128) / p.gp;
+#pragma unroll
+            for (int pn = 0; pn < Cfg::kPanels; ++pn)
+              tma_load_5d(sQ + i * Cfg::kTileBytes + pn * Cfg::kPanelBytes, &p.tm_q, bar_q_full(i), pn * Cfg::kPanelElems, 0, qpos0,
+                          w.slot, bq);
+          }
         }
+        for (int it = 0; it < w.nblocks; ++it) {
+          const int j = w.n_max - 1 - it;
+          int row = w.k_off + j * 128, c3 = p.cu_seqlens_k ? 0 : (p.cache_batch_idx ? p.cache_batch_idx[w.bidb] : w.bidb);
+          if (p.page_size) {
+            const int pos = j * 128;
+            c3 = p.block_table[w.bidb * p.block_table_batch_stride + pos / p.page_size];
+            row = pos % p.page_size;
+          }
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv, ++ring) {
-          const int s = ring % S;
-          const uint32_t ph = (ring / S) & 1;
-          mbar_wait(bar_kv_empty(s), ph ^ 1, 100 + s);
-          mbar_arrive_expect_tx(bar_kv_full(s), Cfg::kTileBytes);
-          const CUtensorMap* tm = kv == 0 ? &p.tm_k : &p.tm_v;
+          for (int kv = 0; kv < 2; ++kv, ++ring) {
+            const int s = ring % S;
+            const uint32_t ph = (ring / S) & 1;
+            mbar_wait(bar_kv_empty(s), ph ^ 1, 100 + s);
+            mbar_arrive_expect_tx(bar_kv_full(s), Cfg::kTileBytes);
+            const CUtensorMap* tm = kv == 0 ? &p.tm_k : &p.tm_v;
 #pragma unroll
-          for (int pn = 0; pn < Cfg::kPanels; ++pn)
-            tma_load_4d(sKV + s * Cfg::kTileBytes + pn * Cfg::kPanelBytes, tm, bar_kv_full(s), pn * Cfg::kPanelElems, row, hk_idx,
-                        c3);
+            for (int pn = 0; pn < Cfg::kPanels; ++pn)
+              tma_load_4d(sKV + s * Cfg::kTileBytes + pn * Cfg::kPanelBytes, tm, bar_kv_full(s), pn * Cfg::kPanelElems, row, w.hk_idx,
+                          c3);
+          }
         }
       }
     }
@@ -317,7 +425,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   }
   // ================================================================== MMA issuer (one elected thread)
   else if (warp == Cfg::kWarpMma) {
-    if (nblocks > 0 && elect_one()) {
+    if (elect_one()) {
       constexpr uint32_t fmt = Elt<T>::kFmt;
       constexpr uint32_t idesc_qk = make_idesc(fmt, fmt, 0, 0, 128, 128);
       constexpr uint32_t idesc_pv = make_idesc(fmt, fmt, 0, 1, 128, kD);
@@ -350,81 +458,136 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         }
       };
 
-      for (int i = 0; i < ntiles; ++i) mbar_wait(bar_q_full(i), 0, 200 + i);
-      // prologue: S_i = Q_i K_0^T
-      mbar_wait(bar_kv_full(0), 0, 210);
-      tc_fence_after();
-      for (int i = 0; i < ntiles; ++i) {
-        issue_qk(i, 0);
-        mma_commit(bar_s_full(i));
-      }
-      mma_commit(bar_kv_empty(0));
-      for (int it = 0; it < nblocks; ++it) {
-        const int ring_v = 2 * it + 1, ring_k = 2 * it + 2;
-        const int sv = ring_v % S, sk_ = ring_k % S;
-        const uint32_t phv = (ring_v / S) & 1, phk = (ring_k / S) & 1;
-        const bool more = it + 1 < nblocks;
-        if (it == 0 && v_tail) mbar_wait(bar_v_clean, 0, 221);  // warp 10 has zeroed the rows beyond seqlen_k
-        else mbar_wait(bar_kv_full(sv), phv, 220);
-        for (int i = 0; i < ntiles; ++i) {
-          mbar_wait(bar_p_full(i), it & 1, 230 + i);
-          FTS(0 + 4 * i);
-          tc_fence_after();
-          issue_pv(i, sv, it > 0, 0);
-          mbar_wait(bar_p_full(i) + 16, it & 1, 232 + i);
-          FTS(1 + 4 * i);
-          tc_fence_after();
-          issue_pv(i, sv, it > 0, 1);
-          mma_commit(bar_o_full(i));
-          FTS(2 + 4 * i);
-          if (i == ntiles - 1) mma_commit(bar_kv_empty(sv));
-          if (more) {
-            if (i == 0) {
-              mbar_wait(bar_kv_full(sk_), phk, 240);
-              tc_fence_after();
-            }
-            issue_qk(i, sk_);
+      int ring = 0, vclean_cnt = 0;
+      int q_items[2] = {0, 0};   // items so far in which tile i had work (Q_i loaded, O_i produced)
+      int blk[2] = {0, 0};       // blocks so far processed by tile i: phase of s_full / p_full / o_full
+      for (int r = 0; r < rounds; ++r) {
+        const int L = item_of_round(r);
+        FwdWork w;
+        if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
+        const int it = 0;  // (FTS below refers to the first item's iterations only)
+        (void)it;
+        bool act[2], first_pv[2];
+#pragma unroll
+        for (int i = 0; i < kTiles; ++i) {
+          act[i] = w.it_hi(i) > w.it_lo(i);
+          first_pv[i] = true;
+          if (act[i]) mbar_wait(bar_q_full(i), q_items[i] & 1, 200 + i);
+        }
+        // prologue: S_i = Q_i K_0^T for the tiles that start with the first streamed block
+        mbar_wait(bar_kv_full(ring % S), (ring / S) & 1, 210);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < kTiles; ++i) {
+          if (act[i] && w.it_lo(i) == 0) {
+            issue_qk(i, ring % S);
             mma_commit(bar_s_full(i));
-            FTS(3 + 4 * i);
-            if (i == ntiles - 1) mma_commit(bar_kv_empty(sk_));
+            if (w.it_hi(i) == 1) mma_commit(bar_q_empty(i));
           }
         }
+        mma_commit(bar_kv_empty(ring % S));
+        for (int it2 = 0; it2 < w.nblocks; ++it2) {
+          const int ring_v = ring + 2 * it2 + 1, ring_k = ring + 2 * it2 + 2;
+          const int sv = ring_v % S, sk_ = ring_k % S;
+          const uint32_t phv = (ring_v / S) & 1, phk = (ring_k / S) & 1;
+          const bool more = it2 + 1 < w.nblocks;
+          if (it2 == 0 && w.v_tail) { mbar_wait(bar_v_clean, vclean_cnt & 1, 221); ++vclean_cnt; }  // rows beyond seqlen_k zeroed
+          else mbar_wait(bar_kv_full(sv), phv, 220);
+          bool k_waited = false;
+          int last_pv = -1, last_qk = -1;
+#pragma unroll
+          for (int i = 0; i < kTiles; ++i) {
+            if (act[i] && it2 >= w.it_lo(i) && it2 < w.it_hi(i)) last_pv = i;
+            if (act[i] && it2 + 1 >= w.it_lo(i) && it2 + 1 < w.it_hi(i)) last_qk = i;
+          }
+#pragma unroll
+          for (int i = 0; i < kTiles; ++i) {
+            if (!act[i]) continue;
+            if (it2 >= w.it_lo(i) && it2 < w.it_hi(i)) {
+              if (first_pv[i]) {   // O_i of the previous item must have been read out by its epilogue
+                if (q_items[i] > 0) mbar_wait(bar_o_free(i), (q_items[i] - 1) & 1, 225 + i);
+              }
+              mbar_wait(bar_p_full(i), blk[i] & 1, 230 + i);
+              tc_fence_after();
+              issue_pv(i, sv, !first_pv[i], 0);
+              mbar_wait(bar_p_full(i) + 16, blk[i] & 1, 232 + i);
+              tc_fence_after();
+              issue_pv(i, sv, !first_pv[i], 1);
+              mma_commit(bar_o_full(i));
+              first_pv[i] = false;
+              ++blk[i];
+              if (i == last_pv) mma_commit(bar_kv_empty(sv));
+            }
+            if (more && it2 + 1 >= w.it_lo(i) && it2 + 1 < w.it_hi(i)) {
+              if (!k_waited) {
+                mbar_wait(bar_kv_full(sk_), phk, 240);
+                tc_fence_after();
+                k_waited = true;
+              }
+              issue_qk(i, sk_);
+              mma_commit(bar_s_full(i));
+              if (it2 + 2 == w.it_hi(i)) mma_commit(bar_q_empty(i));   // that was the item's last read of Q_i
+              if (i == last_qk) mma_commit(bar_kv_empty(sk_));
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kTiles; ++i)
+          if (act[i]) ++q_items[i];
+        ring += 2 * w.nblocks;
       }
     }
     __syncwarp();
   }
   // ================================================================== V-tail cleaner (otherwise idle warp)
   else if (warp == Cfg::kWarpClean) {
-    if (nblocks > 0 && v_tail) {
-      // Rows of the last V block beyond seqlen_k may hold garbage (kv-cache tail, next sequence): P is
-      // exactly 0 there but 0 * NaN would poison O, so clear them before the first PV
-      // (reference: Clear_OOB_MN on the V load, flash_fwd_kernel.h:254-262).
-      mbar_wait(bar_kv_full(1), 0, 250);
-      const int valid = sk_b - (nblk_total - 1) * 128;
-      const int nvec = (128 - valid) * 8;
-      for (int pn = 0; pn < Cfg::kPanels; ++pn) {
-        uint4* base = reinterpret_cast<uint4*>(smem_gen + Cfg::kSmemQ + 1 * Cfg::kTileBytes + pn * Cfg::kPanelBytes +
-                                               valid * 128);
-        for (int x = lane; x < nvec; x += 32) base[x] = make_uint4(0, 0, 0, 0);
+    int ring = 0;
+    for (int r = 0; r < rounds; ++r) {
+      const int L = item_of_round(r);
+      FwdWork w;
+      if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
+      if (w.v_tail) {
+        // Rows of the last V block beyond seqlen_k may hold garbage (kv-cache tail, next sequence): P is
+        // exactly 0 there but 0 * NaN would poison O, so clear them before the first PV
+        // (reference: Clear_OOB_MN on the V load, flash_fwd_kernel.h:254-262).
+        const int rv = ring + 1;
+        mbar_wait(bar_kv_full(rv % S), (rv / S) & 1, 250);
+        const int valid = w.sk_b - (w.nblk_total - 1) * 128;
+        const int nvec = (128 - valid) * 8;
+        for (int pn = 0; pn < Cfg::kPanels; ++pn) {
+          uint4* base = reinterpret_cast<uint4*>(smem_gen + Cfg::kSmemQ + (rv % S) * Cfg::kTileBytes + pn * Cfg::kPanelBytes +
+                                                 valid * 128);
+          for (int x = lane; x < nvec; x += 32) base[x] = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_v_clean);
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_v_clean);
+      ring += 2 * w.nblocks;
     }
   }
   } else {
   // ================================================================== softmax warpgroups
     reg_alloc<Cfg::kRegsSoftmax>();
     const int tile = warp >> 2;
-    if (tile < ntiles) {
-      const int wq = warp & 3;
-      const uint32_t lane_sel = uint32_t(wq * 32) << 16;
-      const uint32_t tS = tmem_base + lane_sel + tile * 128;
-      const uint32_t tO = tmem_base + lane_sel + kTiles * 128 + tile * kD;
-      const int r = row0 + tile * 128 + wq * 32 + lane;  // packed row of this thread
-      const int qpos = r / p.gp;
-      const int head = slot * p.gp + (r - qpos * p.gp);
-      const bool row_valid = r < rows_total;
+    const int wq = warp & 3;
+    const uint32_t lane_sel = uint32_t(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + tile * 128;
+    const uint32_t tO = tmem_base + lane_sel + kTiles * 128 + tile * kD;
+    int blk = 0;   // blocks processed so far by this tile (phase of s_full / o_full)
+    for (int r = 0; r < rounds; ++r) {
+      const int L = item_of_round(r);
+      FwdWork w;
+      if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w)) continue;
+      if (tile >= w.ntiles) continue;
+      const int bidb = w.bidb, split = w.split, slot = w.slot, hk_idx = w.hk_idx, shift = w.shift;
+      const int row0 = w.row0, rows_total = w.rows_total, sk_b = w.sk_b, q_off = w.q_off;
+      const int it_lo = w.it_lo(tile), it_hi = w.it_hi(tile);
+      const int nblocks = it_hi - it_lo;   // blocks of THIS tile
+      const int rr = row0 + tile * 128 + wq * 32 + lane;  // packed row of this thread
+      const int qpos = rr / p.gp;
+      const int head = slot * p.gp + (rr - qpos * p.gp);
+      const bool row_valid = rr < rows_total;
       // fp8: S = (q*qd).(k*kd) -> fold the de-scales into the softmax scale; O picks up vd in the epilogue
       float descale_qk = 1.f, descale_v = 1.f;
       if constexpr (kFp8) {
@@ -455,11 +618,11 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + head] / scale_eff;
 
       float m_ref = kNegInf, row_sum = 0.f;
-      for (int it = 0; it < nblocks; ++it) {
-        const int j = n_max - 1 - it;
+      for (int it = it_lo; it < it_hi; ++it, ++blk) {
+        const int j = w.n_max - 1 - it;
         const int col0 = j * 128;
-        mbar_wait(bar_s_full(tile), it & 1, 300 + tile);
-        if (wq == 0 && lane == 0) FTS(8 + 4 * tile);
+        mbar_wait(bar_s_full(tile), blk & 1, 300 + tile);
+        if (wq == 0 && lane == 0 && r == 0) FTS(8 + 4 * tile);
         tc_fence_after();
         uint32_t su[128];
         float* s = reinterpret_cast<float*>(su);
@@ -468,7 +631,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         if (p.has_right) need_mask |= col0 + 128 > t_qlo + 1 + shift + p.wr;
         if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
         const bool slow = need_mask || has_softcap || p.alibi_slopes != nullptr ||
-                          (p.debug_s != nullptr && it == 0);
+                          (p.debug_s != nullptr && it == 0 && r == 0);
         float mx;
         if (!slow) {
           // fast path: second half of the row streams out of TMEM while the first half is reduced
@@ -503,7 +666,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           tmem_ld_x32(tS + 64, su + 64);
           tmem_ld_x32(tS + 96, su + 96);
           tmem_wait_ld();
-          if (p.debug_s && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile == 0 && it == 0) {
+          if (p.debug_s && blockIdx.x == 0 && r == 0 && tile == 0 && it == 0) {
 #pragma unroll
             for (int c = 0; c < 128; ++c) p.debug_s[(wq * 32 + lane) * 128 + c] = s[c];
           }
@@ -530,9 +693,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           mx = fmax3(m0, m1, fmaxf(s[126], s[127]));
         }
         // ---- online softmax: row max with a lazily updated reference (exact after normalisation)
-        if (wq == 0 && lane == 0) FTS(9 + 4 * tile);
+        if (wq == 0 && lane == 0 && r == 0) FTS(9 + 4 * tile);
         const float m_new = fmaxf(m_ref, mx);
-        if (it == 0) {
+        if (it == it_lo) {
           m_ref = m_new;
         } else {
           bool need = (m_new - m_ref) * scale_log2 > kLagLog2;  // NaN (-inf - -inf) compares false
@@ -541,7 +704,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
             need = false;
           }
           if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(bar_o_full(tile), (it - 1) & 1, 310 + tile);  // PV of the previous block has landed
+            mbar_wait(bar_o_full(tile), (blk - 1) & 1, 310 + tile);  // PV of the previous block has landed
             tc_fence_after();
             const float f = need ? ex2((m_ref - m_new) * scale_log2) : 1.0f;
 #pragma unroll
@@ -559,7 +722,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         }
         const float neg_ms = (m_ref == kNegInf) ? kPOffset : kPOffset - m_ref * scale_log2;
         // ---- P = exp2(S*scale_log2 - m*scale_log2), written back over S as packed 16-bit.
-        // Packed FFMA2 for the scaling; kPolyPairs of every 4 pairs take the FMA-pipe polynomial instead
+        // Packed FFMA2 for the scaling; a share of the pairs takes the FMA-pipe polynomial instead
         // of MUFU.EX2 (the MUFU unit, 16 op/clk/SM, is otherwise as busy as the tensor pipe).
         const uint64_t sc2 = pack2(scale_log2, scale_log2), ng2 = pack2(neg_ms, neg_ms);
         uint64_t acc_a = pack2(0.f, 0.f), acc_b = pack2(0.f, 0.f);
@@ -691,62 +854,48 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         // (softmax.h:180, flash_fwd_kernel.h:544-582)
         lse_val = p.num_splits > 1 ? kNegInf : INFINITY;
       }
+      uint32_t o[kD] = {};   // the whole O row leaves TMEM first, so that the next item's P V may overwrite it (zeros if the
+                             // tile had no visible block: a maybe-uninitialised array would be demoted to local memory)
       if (nblocks > 0) {
-        mbar_wait(bar_o_full(tile), (nblocks - 1) & 1, 320 + tile);
+        mbar_wait(bar_o_full(tile), (blk - 1) & 1, 320 + tile);
         tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < kD; cc += 32) tmem_ld_x32(tO + cc, o + cc);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_o_free(tile));
       }
       if (p.num_splits > 1) {
         const int64_t prow = ((int64_t(split) * p.b + bidb) * p.h + head) * p.sq + qpos;
         float* dst = p.o_accum + prow * kD;
+        if (row_valid) {
 #pragma unroll
-        for (int cc = 0; cc < kD; cc += 32) {
-          uint32_t o[32];
-          if (nblocks > 0) {
-            tmem_ld_x32(tO + cc, o);
-            tmem_wait_ld();
+          for (int c = 0; c < kD; c += 4) {
+            float4 v4;
+            v4.x = __uint_as_float(o[c]) * inv;
+            v4.y = __uint_as_float(o[c + 1]) * inv;
+            v4.z = __uint_as_float(o[c + 2]) * inv;
+            v4.w = __uint_as_float(o[c + 3]) * inv;
+            *reinterpret_cast<float4*>(dst + c) = v4;
           }
-          if (row_valid) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              float4 v4;
-              v4.x = nblocks > 0 ? __uint_as_float(o[c]) * inv : 0.f;
-              v4.y = nblocks > 0 ? __uint_as_float(o[c + 1]) * inv : 0.f;
-              v4.z = nblocks > 0 ? __uint_as_float(o[c + 2]) * inv : 0.f;
-              v4.w = nblocks > 0 ? __uint_as_float(o[c + 3]) * inv : 0.f;
-              *reinterpret_cast<float4*>(dst + cc + c) = v4;
-            }
-          }
+          p.lse_accum[prow] = lse_val;
         }
-        if (row_valid) p.lse_accum[prow] = lse_val;
       } else {
         OutT* dst = reinterpret_cast<OutT*>(p.o) + (p.cu_seqlens_q ? 0 : bidb * p.o_batch_stride) +
                  int64_t(q_off + qpos) * p.o_row_stride + int64_t(head) * p.o_head_stride;
+        if (row_valid) {
 #pragma unroll
-        for (int cc = 0; cc < kD; cc += 32) {
-          uint32_t o[32];
-          if (nblocks > 0) {
-            tmem_ld_x32(tO + cc, o);
-            tmem_wait_ld();
-          }
-          if (row_valid) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              if (cc + c < p.d) {  // d is a multiple of 8
-                uint4 v4;
-                if (nblocks > 0) {
-                  v4.x = Elt<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
-                  v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
-                  v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
-                  v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
-                } else {
-                  v4 = make_uint4(0, 0, 0, 0);
-                }
-                *reinterpret_cast<uint4*>(dst + cc + c) = v4;
-              }
+          for (int c = 0; c < kD; c += 8) {
+            if (c < p.d) {  // d is a multiple of 8
+              uint4 v4;
+              v4.x = Elt<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+              v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+              v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+              v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c) = v4;
             }
           }
-        }
-        if (row_valid) {
           if (p.cu_seqlens_q) p.lse[int64_t(head) * p.total_q + q_off + qpos] = lse_val;
           else p.lse[(int64_t(bidb) * p.h + head) * p.sq + qpos] = lse_val;
         }

@@ -42,7 +42,12 @@ def load():
             import warnings
 
             warnings.warn(f"flash_attn_2_cuda extension is older than its sources and could not be rebuilt ({e}); loading it as is")
-    spec = importlib.util.spec_from_file_location("flash_attn_2_cuda", path)
+    # The shared object's init symbol is PyInit_flash_attn_2_cuda (put flash_attention_b200/ext on sys.path and a plain
+    # `import flash_attn_2_cuda` works).  Here it is imported under a qualified spec name: pybind11 >= 3 caches extension
+    # modules per interpreter BY SPEC NAME, so with the reference's own flash_attn_2_cuda wheel already imported in the
+    # same process (the parity tests run both side by side) a second spec called "flash_attn_2_cuda" would silently
+    # return the reference's module object instead of initialising this one.
+    spec = importlib.util.spec_from_file_location("flash_attention_b200.ext.flash_attn_2_cuda", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     _MOD = mod

@@ -115,6 +115,16 @@ def flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, wi
         out, lse = _op.fwd_fp8(_c(q), _c(k), _c(v), None, q_descale, k_descale, v_descale, softmax_scale, causal,
                                window_size[0], window_size[1], softcap, alibi_slopes)
         return (out, lse, None) if return_attn_probs else out
+    if not _tracing() and not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)):
+        # inference fast path: no autograd node, straight into the compiled module
+        d = q.shape[-1]
+        if softmax_scale is None:
+            softmax_scale = d ** (-0.5)
+        qp, kp, vp = (_c(_pad8(t, d)) for t in (q, k, v))
+        out_p, lse, S_dmask, _ = _op.fwd(qp, kp, vp, None, alibi_slopes, dropout_p, softmax_scale, causal, window_size[0],
+                                         window_size[1], softcap, return_attn_probs and dropout_p > 0, None)
+        out = out_p if d % 8 == 0 else out_p[..., :d]
+        return (out, lse, S_dmask) if return_attn_probs else out
     return _FlashAttnFunc.apply(q, k, v, dropout_p, softmax_scale, causal, tuple(window_size), softcap, alibi_slopes,
                                 deterministic, return_attn_probs)
 

@@ -29,8 +29,7 @@ def fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dropout_p: float, sof
         return_softmax: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     out, lse, p, rng_state = _op.fwd(q, k, v, None, alibi_slopes, dropout_p, softmax_scale, causal, window_size_left,
                                      window_size_right, softcap, return_softmax, None)
-    # custom-op outputs must be fresh tensors: the module hands out shared placeholders for `p` / `rng_state` when unused
-    return out, lse, (p if return_softmax else p.new_empty((0,))), (rng_state if dropout_p > 0 else rng_state.clone())
+    return out, lse, p, rng_state
 
 
 @fwd.register_fake
@@ -52,7 +51,7 @@ def varlen_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: 
     out, lse, p, rng_state = _op.varlen_fwd(q, k, v, None, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k, block_table,
                                             alibi_slopes, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale, zero_tensors,
                                             causal, window_size_left, window_size_right, softcap, return_softmax, None)
-    return out, lse, (p if return_softmax else p.new_empty((0,))), (rng_state if dropout_p > 0 else rng_state.clone())
+    return out, lse, p, rng_state
 
 
 @varlen_fwd.register_fake

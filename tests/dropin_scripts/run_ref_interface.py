@@ -22,6 +22,7 @@ kind, path = sys.argv[1], sys.argv[2]
 def load(name):
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod   # torch.compile re-imports the module of a traced function by name
     spec.loader.exec_module(mod)
     return mod
 
@@ -71,11 +72,14 @@ if kind == "fa2":
         ro, _ = attention_oracle(qd[i:i + 1].cpu(), kk, vv_, causal=True)
         close(o[i:i + 1], ro, 2e-2, f"kvcache[{i}]")
     # torch.compile(fullgraph=True) through the REFERENCE's custom ops + fakes on our kernels (a4)
-    def step(q, k, v, do):
-        out = iface.flash_attn_func(q, k, v, causal=True)
+    def fwd_only(q, k, v):
+        return iface.flash_attn_func(q, k, v, causal=True)
+
+    def step(f, q, k, v, do):
+        out = f(q, k, v)
         return (out,) + torch.autograd.grad(out, (q, k, v), do)
-    eager = step(q, k, v, do)
-    comp = torch.compile(step, fullgraph=True)(q, k, v, do)
+    eager = step(fwd_only, q, k, v, do)
+    comp = step(torch.compile(fwd_only, fullgraph=True), q, k, v, do)
     for a, c in zip(eager, comp):
         assert (a.float() - c.float()).abs().max().item() <= 2e-2
     print("OK fa2 interface", getattr(iface, "__file__", path))

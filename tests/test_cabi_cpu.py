@@ -93,8 +93,10 @@ def test_forward_plan_host_logic(fa_lib):
     # long prefill against a cache: no packing, 256-row CTAs (2-tile kernel) for the non-causal stream
     splits, gp, mblocks = op.plan_kvcache(4, 8192, 8192, 16, 16, 128, 0, False, -1, -1)
     assert (splits, gp, mblocks) == (1, 1, 8192 // 256)
-    # causal at the same size takes the 1-tile kernel (measured faster up to 16k): 128-row CTAs
-    assert op.plan_kvcache(4, 8192, 8192, 16, 16, 128, 0, True, -1, -1)[2] == 8192 // 128
+    # causal at the same size: 2-tile work items too since the forward became persistent (round 1: 1-tile up to 16k)
+    assert op.plan_kvcache(4, 8192, 8192, 16, 16, 128, 0, True, -1, -1)[2] == 8192 // 256
+    # short causal problems keep the 1-tile kernel (two CTAs per SM)
+    assert op.plan_kvcache(32, 1024, 1024, 16, 16, 128, 0, True, -1, -1)[2] == 1024 // 128
     # few CTAs and a long KV: split heuristic kicks in (flash_api.cpp:281-315 rule on 2 x 148 CTA slots)
     splits, gp, mblocks = op.plan_kvcache(1, 1, 16384, 8, 8, 128, 0, False, -1, -1)
     assert splits > 1
@@ -198,7 +200,7 @@ def test_compiled_operator_module_surface_and_host_checks():
     mod = fab.install()
     import flash_attn_2_cuda as installed
 
-    assert installed is mod and mod.__file__.endswith(".so") and mod.__name__ == "flash_attn_2_cuda"
+    assert installed is mod and mod.__file__.endswith(".so") and mod.__name__.endswith("flash_attn_2_cuda")
     for name in ("fwd", "varlen_fwd", "bwd", "varlen_bwd", "fwd_kvcache", "fwd_fp8", "fwd_ex", "fwd_combine", "plan_kvcache"):
         assert callable(getattr(mod, name)), name
     doc = mod.varlen_fwd.__doc__

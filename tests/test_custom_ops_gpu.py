@@ -23,14 +23,16 @@ def test_torch_compile_fullgraph_dense(fab, causal):
     q, k, v = make_qkv(2, 384, 512, 4, 2, 128)
     do = torch.randn_like(q)
 
-    def step(q, k, v, do):
-        out = fab.flash_attn_func(q, k, v, causal=causal, window_size=(-1, -1))
-        dq, dk, dv = torch.autograd.grad(out, (q, k, v), do)
-        return out, dq, dk, dv
+    def fwd(q, k, v):
+        return fab.flash_attn_func(q, k, v, causal=causal, window_size=(-1, -1))
+
+    def step(f, q, k, v, do):   # the forward graph is captured whole; its backward is the AOT-generated graph of the same ops
+        out = f(q, k, v)
+        return (out,) + torch.autograd.grad(out, (q, k, v), do)
 
     qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
-    eager = step(qg, kg, vg, do)
-    compiled = torch.compile(step, fullgraph=True)(qg, kg, vg, do)
+    eager = step(fwd, qg, kg, vg, do)
+    compiled = step(torch.compile(fwd, fullgraph=True), qg, kg, vg, do)
     assert torch.equal(eager[0], compiled[0])   # same forward kernel on the same inputs: bitwise equal
     for a, b in zip(eager[1:], compiled[1:]):   # dQ partials are reduce-added in launch order: equal up to fp32 rounding
         assert (a.float() - b.float()).abs().max().item() <= 2e-2
@@ -45,12 +47,15 @@ def test_torch_compile_fullgraph_varlen(fab):
     v = torch.randn(387, hk, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
     do = torch.randn(387, h, d, device="cuda", dtype=torch.bfloat16)
 
-    def step(q, k, v, do):
-        out = fab.flash_attn_varlen_func(q, k, v, cu, cu, max(lens), max(lens), causal=True)
+    def fwd(q, k, v):
+        return fab.flash_attn_varlen_func(q, k, v, cu, cu, max(lens), max(lens), causal=True)
+
+    def step(f, q, k, v, do):
+        out = f(q, k, v)
         return (out,) + torch.autograd.grad(out, (q, k, v), do)
 
-    eager = step(q, k, v, do)
-    compiled = torch.compile(step, fullgraph=True)(q, k, v, do)
+    eager = step(fwd, q, k, v, do)
+    compiled = step(torch.compile(fwd, fullgraph=True), q, k, v, do)
     for a, b in zip(eager, compiled):
         assert (a.float() - b.float()).abs().max().item() <= 2e-2
 

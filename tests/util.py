@@ -87,5 +87,9 @@ def load_reference_fa2():
                 sys.modules.pop("flash_attn_2_cuda", None)
         if not getattr(mod, "__file__", "").endswith(".so"):
             pytest.skip("flash_attn_2_cuda resolves to a non-compiled module")
+        # it must really be the reference's binary, not this package's module under the same name (pybind11 >= 3 caches
+        # extension modules by spec name: see flash_attention_b200/flash_attn_2_cuda.py)
+        assert not hasattr(mod, "fwd_fp8") and "flash_attention_b200" not in mod.__file__, \
+            f"flash_attn_2_cuda resolved to this package's own module: {mod.__file__}"
         _REAL_FA2 = mod
     return _REAL_FA2

@@ -24,9 +24,11 @@ def bench(name, f, n=3000):
     t0 = time.perf_counter()
     for _ in range(n):
         f()
-    t1 = time.perf_counter()   # host time to ENQUEUE n calls (the GPU runs behind; the queue never fills at this size)
+    t1 = time.perf_counter()   # host time to ENQUEUE n calls
     torch.cuda.synchronize()
-    print(f"{name}: {(t1 - t0) / n * 1e6:.1f} us per call (host enqueue)", flush=True)
+    t2 = time.perf_counter()   # ... and until the GPU has finished them (if this is much larger the launch queue was full
+    #                            and the enqueue figure is a GPU-bound number, not host overhead)
+    print(f"{name}: {(t1 - t0) / n * 1e6:.1f} us per call host enqueue, {(t2 - t0) / n * 1e6:.1f} us incl. GPU drain", flush=True)
 
 
 def fb():
@@ -41,4 +43,3 @@ bench("operator module fwd (allocates out)", lambda: op.fwd(q, k, v, None, None,
 with torch.no_grad():
     bench("public flash_attn_func (no grad)", lambda: fa.flash_attn_func(q, k, v, causal=True))
 bench("public flash_attn_func forward + backward (autograd)", fb, 1500)
-os.environ["FA_B200_TMAP_CACHE"] = "0"
