@@ -291,6 +291,9 @@ def main():
                 "frac_of_nominal_2250": achieved / 2250.0, "ms_per_launch": kms}
 
     # ---- e2e: host (pinned) buffers -> H2D -> public API -> D2H of out (+ grads)
+    from flash_attention_b200.host_pipeline import bind_to_device_numa_node
+
+    numa = bind_to_device_numa_node(dev)   # pinned buffers below are first-touched on the GPU's own NUMA node
     hq, hk_, hv, hdo = (torch.empty(t_.shape, dtype=t_.dtype).pin_memory() for t_ in (qd, kd, vd, do))
     for dst, src in ((hq, qd), (hk_, kd), (hv, vd), (hdo, do)):
         dst.copy_(src)
@@ -323,7 +326,7 @@ def main():
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e = {"value": world * fl / (ems.item() * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": ems.item()}
+           "d2h_bytes_per_step": d2h, "ms_per_step": ems.item(), "numa": numa}
 
     if rank == 0:
         cb = None

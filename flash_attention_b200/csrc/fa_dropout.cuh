@@ -2,13 +2,17 @@
 // debug kernel (reference: csrc/flash_attn/src/dropout.h:15-93, philox.cuh:29-51 -- Philox4x32 with 7 rounds,
 // one byte of randomness per attention element, keep iff byte <= floor(p_keep * 255)).
 //
-// Mapping (ours, not FA2's thread-layout-dependent one): one Philox call covers a 4 x 4 patch of the
-// (query, key) matrix of one (batch, head):
-//     counter = (query / 4, key / 4, batch * h + head, offset_lo)     key = (seed_lo, seed_hi ^ offset_hi)
-//     output word (query % 4), byte (key % 4)  ->  the element's random byte
-// so a forward thread (one query, 128 keys) and a backward thread (one key, 64 queries) both use a quarter
-// of every call they make, and the mask is a pure function of (seed, offset, batch, head, query, key):
-// the backward regenerates it from rng_state, the CPU oracle restates it (oracle/attention_oracle.py:philox_keep_mask).
+// Mapping = the REFERENCE's stream, bit for bit (dropout.h:20-47, philox.cuh:29-51), so that the same (seed, offset)
+// drops the same elements as the reference's FA2 kernels (pinned on the GPU against the sign pattern of their S_dmask:
+// tests/test_dropout_gpu.py).  FA2 draws one Philox4x32-7 value per thread and 16 x 32 (query x key) block of its
+// mma.sync m16n8k16 accumulator; written out per ELEMENT (query R, key C) of head bh = batch * h + head:
+//     counter = (lo, hi of [offset + bh * 32 + lane],  R / 16,  C / 32)        key = (seed_lo, seed_hi)
+//     lane    = (R % 8) * 4 + (C % 8) / 2                                      (the accumulator's owner thread)
+//     byte    = ((C % 32) / 16) * 8 + ((C % 16) / 8) * 4 + (C % 2) + 2 * ((R % 16) / 8)   of the 16 output bytes
+// keep iff byte <= floor(p_keep * 255).  A forward thread here owns one query row: per 32 keys it makes 4 calls (the 4
+// lanes of its row) and uses 8 bytes of each; a backward thread owns one key: per 16 queries it makes 8 calls and uses 2
+// bytes of each.  The mask is a pure function of (seed, offset, batch, head, query, key): the backward regenerates it from
+// rng_state, the CPU oracle restates it (oracle/attention_oracle.py:philox_keep_mask).
 #pragma once
 #include <cstdint>
 
@@ -36,13 +40,50 @@ __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t
   return make_uint4(c0, c1, c2, c3);
 }
 
-// the 4 x 4 patch (q4 = query / 4, k4 = key / 4) of head `bh`: word i = query 4*q4 + i, byte j = key 4*k4 + j
-__device__ __forceinline__ uint4 dropout_patch(const DropoutParams& dp, uint32_t q4, uint32_t k4, uint32_t bh) {
-  return philox4x32_7(q4, k4, bh, dp.off_lo, dp.seed_lo, dp.seed_hi ^ dp.off_hi);
+// the reference's draw for accumulator-owner `lane` of the 16 x 32 block (row_blk, col_blk) of head `bh`
+__device__ __forceinline__ uint4 dropout_draw(const DropoutParams& dp, uint32_t row_blk, uint32_t col_blk, uint32_t bh, uint32_t lane) {
+  const uint64_t off = ((uint64_t(dp.off_hi) << 32) | dp.off_lo) + uint64_t(bh) * 32u + lane;
+  return philox4x32_7(uint32_t(off), uint32_t(off >> 32), row_blk, col_blk, dp.seed_lo, dp.seed_hi);
 }
-
-__device__ __forceinline__ uint32_t select_word(const uint4& r, int i) {
-  return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w));
+__device__ __forceinline__ uint32_t draw_byte(const uint4& r, int idx) {   // byte `idx` (0..15) of the 16 output bytes
+  const uint32_t w = (idx >> 2) == 0 ? r.x : ((idx >> 2) == 1 ? r.y : ((idx >> 2) == 2 ? r.z : r.w));
+  return (w >> (8 * (idx & 3))) & 0xffu;
+}
+// one element (slow path: S_dmask checker kernel)
+__device__ __forceinline__ bool dropout_keep(const DropoutParams& dp, uint32_t R, uint32_t C, uint32_t bh) {
+  const uint4 r = dropout_draw(dp, R >> 4, C >> 5, bh, (R & 7u) * 4u + ((C & 7u) >> 1));
+  const int idx = int(((C & 31u) >> 4) * 8u + ((C & 15u) >> 3) * 4u + (C & 1u) + 2u * ((R & 15u) >> 3));
+  return draw_byte(r, idx) <= dp.thr;
+}
+// forward thread (one query row R): keep bits of the 32 keys [32 * col_blk, 32 * col_blk + 32), bit c = key offset c
+__device__ __forceinline__ uint32_t dropout_keep_row32(const DropoutParams& dp, uint32_t R, uint32_t col_blk, uint32_t bh) {
+  uint32_t keep = 0;
+  const int vhi = int((R & 15u) >> 3) * 2;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint4 r = dropout_draw(dp, R >> 4, col_blk, bh, (R & 7u) * 4u + uint32_t(t));
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          keep |= (draw_byte(r, jj * 8 + a * 4 + e + vhi) <= dp.thr ? 1u : 0u) << (jj * 16 + a * 8 + 2 * t + e);
+  }
+  return keep;
+}
+// backward thread (one key C): keep bits of the 16 queries [16 * row_blk, 16 * row_blk + 16), bit r = query offset r
+__device__ __forceinline__ uint32_t dropout_keep_col16(const DropoutParams& dp, uint32_t row_blk, uint32_t C, uint32_t bh) {
+  uint32_t keep = 0;
+  const int base = int(((C & 31u) >> 4) * 8u + ((C & 15u) >> 3) * 4u + (C & 1u));
+  const uint32_t t = (C & 7u) >> 1;
+#pragma unroll
+  for (int gq = 0; gq < 8; ++gq) {
+    const uint4 r = dropout_draw(dp, row_blk, C >> 5, bh, uint32_t(gq) * 4u + t);
+    keep |= (draw_byte(r, base) <= dp.thr ? 1u : 0u) << gq;
+    keep |= (draw_byte(r, base + 2) <= dp.thr ? 1u : 0u) << (gq + 8);
+  }
+  return keep;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -92,11 +133,10 @@ __global__ void __launch_bounds__(256) fa_dmask_kernel(const DmaskParams p) {
       for (int c = 0; c < p.d; ++c) acc = fmaf(float(qrow[c]), float(krow[c]), acc);
       acc = acc * p.scale - slope * fabsf(float(i + shift - j));
       val = __expf(acc - lse);
-      const uint4 r = dropout_patch(p.drop, uint32_t(i) >> 2, uint32_t(j) >> 2, uint32_t(bidb * p.h + head));
-      const uint32_t byte = (select_word(r, i & 3) >> (8 * (j & 3))) & 0xffu;
+      const bool keep = dropout_keep(p.drop, uint32_t(i), uint32_t(j), uint32_t(bidb * p.h + head));
       // dropped: negative sign.  A probability that underflows to 0 (in fp32, or when cast to fp16) would lose the sign
       // (-0.0 >= 0 is true), so a dropped entry is stored as at most -2^-24 (smallest fp16 subnormal, exact in bf16 too)
-      if (byte > p.drop.thr) val = -fmaxf(val, 5.9604645e-8f);
+      if (!keep) val = -fmaxf(val, 5.9604645e-8f);
     }
     out[j] = T(val);
   }

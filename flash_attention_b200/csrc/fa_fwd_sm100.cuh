@@ -807,11 +807,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
             if constexpr (kDropout) {
               // the row sum keeps the undropped probabilities (softmax.h:128-187 runs before dropout.h:apply_dropout);
               // only the P that feeds P V is thinned, and 1/p_keep is folded into the final normalisation
-              if ((c & 2) == 0)
-                keep_w = select_word(dropout_patch(p.drop, uint32_t(qpos) >> 2, uint32_t(col0 + cc + c) >> 2,
-                                                   uint32_t(bidb * p.h + head)), qpos & 3);
-              e0 = ((keep_w >> (8 * (c & 2))) & 0xffu) <= p.drop.thr ? e0 : 0.f;
-              e1 = ((keep_w >> (8 * (c & 2) + 8)) & 0xffu) <= p.drop.thr ? e1 : 0.f;
+              if (c == 0) keep_w = dropout_keep_row32(p.drop, uint32_t(qpos), uint32_t(col0 + cc) >> 5, uint32_t(bidb * p.h + head));
+              e0 = ((keep_w >> c) & 1u) ? e0 : 0.f;
+              e1 = ((keep_w >> (c + 1)) & 1u) ? e1 : 0.f;
             }
             if constexpr (kFp8) {
               ee[c & 2] = e0;

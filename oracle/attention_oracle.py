@@ -216,29 +216,35 @@ def philox4x32_7(c0, c1, c2, c3, k0, k1, rounds: int = 7):
 
 
 def philox_keep_mask(seed: int, offset: int, p_dropout: float, b: int, h: int, sq: int, sk: int) -> torch.Tensor:
-    """The library's dropout mask, restated on the CPU: (b, h, sq, sk) bool, True = keep.
+    """The dropout mask of the reference's kernels, restated on the CPU: (b, h, sq, sk) bool, True = keep.
 
-    Mapping (flash_attention_b200/csrc/fa_dropout.cuh): one Philox call per 4x4 patch of the (query, key)
-    matrix of a (batch, head): counter = (query//4, key//4, batch*h + head, offset_lo), key = (seed_lo,
-    seed_hi ^ offset_hi); output word (query % 4), byte (key % 4) is the element's random byte; keep iff
-    byte <= floor((1 - p_dropout) * 255) (8-bit threshold: csrc/flash_attn/src/dropout.h:17)."""
+    FA2 draws one Philox4x32-7 value per thread and 16 x 32 (query x key) block of its mma.sync accumulator
+    (csrc/flash_attn/src/dropout.h:20-47, philox.cuh:29-51); per element (query R, key C) of head bh = batch * h + head:
+        counter = (lo, hi of [offset + bh * 32 + lane], R // 16, C // 32),  key = (seed_lo, seed_hi)
+        lane    = (R % 8) * 4 + (C % 8) // 2
+        byte    = ((C % 32) // 16) * 8 + ((C % 16) // 8) * 4 + (C % 2) + 2 * ((R % 16) // 8)   of the 16 output bytes
+    keep iff byte <= floor((1 - p_dropout) * 255) (8-bit threshold, dropout.h:17).  The library's kernels use the same
+    stream (flash_attention_b200/csrc/fa_dropout.cuh); on the GPU box the mask is also compared with the sign pattern of
+    the S_dmask the reference's own FA2 binary returns for the same (seed, offset) (tests/test_dropout_gpu.py)."""
     import numpy as np
 
     seed &= 2**64 - 1
     offset &= 2**64 - 1
     thr = int(np.floor(np.float32(1.0 - p_dropout) * np.float32(255.0)))
-    nq4, nk4 = (sq + 3) // 4, (sk + 3) // 4
+    R = np.arange(sq, dtype=np.uint64).reshape(1, -1, 1)
+    C = np.arange(sk, dtype=np.uint64).reshape(1, 1, -1)
     bh = np.arange(b * h, dtype=np.uint64).reshape(-1, 1, 1)
-    q4 = np.arange(nq4, dtype=np.uint64).reshape(1, -1, 1)
-    k4 = np.arange(nk4, dtype=np.uint64).reshape(1, 1, -1)
-    shape = (b * h, nq4, nk4)
-    words = philox4x32_7(np.broadcast_to(q4, shape), np.broadcast_to(k4, shape), np.broadcast_to(bh, shape),
-                         np.full(shape, offset & 0xFFFFFFFF, dtype=np.uint64), seed & 0xFFFFFFFF,
-                         ((seed >> 32) ^ (offset >> 32)) & 0xFFFFFFFF)
-    # (bh, q4, k4, word=query%4, byte=key%4)
-    w = np.stack(words, axis=-1)
-    by = np.stack([(w >> np.uint64(8 * j)) & np.uint64(0xFF) for j in range(4)], axis=-1)
-    keep = (by <= np.uint64(thr)).transpose(0, 1, 3, 2, 4).reshape(b * h, nq4 * 4, nk4 * 4)[:, :sq, :sk]
+    shape = (b * h, sq, sk)
+    lane = (R % 8) * 4 + (C % 8) // 2
+    off = (np.uint64(offset) + bh * np.uint64(32) + lane) & np.uint64(2**64 - 1)
+    off = np.broadcast_to(off, shape)
+    words = philox4x32_7(off & np.uint64(0xFFFFFFFF), off >> np.uint64(32), np.broadcast_to(R // 16, shape),
+                         np.broadcast_to(C // 32, shape), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    idx = np.broadcast_to(((C % 32) // 16) * 8 + ((C % 16) // 8) * 4 + (C % 2) + 2 * ((R % 16) // 8), shape).astype(np.int64)
+    w = np.stack(words, axis=-1)                                    # (bh, sq, sk, 4) 32-bit words
+    word = np.take_along_axis(w, (idx // 4)[..., None], axis=-1)[..., 0]
+    byte = (word >> (np.uint64(8) * (idx % 4).astype(np.uint64))) & np.uint64(0xFF)
+    keep = byte <= np.uint64(thr)
     return torch.from_numpy(np.ascontiguousarray(keep)).view(b, h, sq, sk)
 
 

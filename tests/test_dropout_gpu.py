@@ -191,3 +191,42 @@ def test_dropout_argument_errors(fab):
         op.fwd(q, k, v, None, None, 0.0, 0.125, False, -1, -1, 0.0, True, None)
     with pytest.raises(RuntimeError, match="p_dropout"):
         op.fwd(q, k, v, None, None, 1.0, 0.125, False, -1, -1, 0.0, False, None)
+
+
+@pytest.mark.parametrize("b,sq,sk,h,hk,d,causal,p", [
+    (2, 256, 256, 4, 4, 128, False, 0.17),
+    (1, 384, 500, 4, 2, 128, True, 0.3),      # GQA, sq != sk, causal (bottom-right aligned)
+    (2, 130, 257, 3, 3, 64, False, 0.17),     # ragged sizes, head dim 64
+    (1, 200, 333, 2, 1, 96, True, 0.5),
+])
+def test_dropout_mask_is_the_reference_kernels_mask(fab, b, sq, sk, h, hk, d, causal, p):
+    """Same CUDA generator state -> the SAME elements dropped as by the reference's FA2 kernels (the flash_attn wheel in
+    the image): the dropout stream is the reference's (dropout.h:20-47), not a look-alike.  FA2 returns S_dmask with a
+    negative sign where an element was dropped ("for testing only", flash_attn_interface.py:1196), in plain (query, key)
+    layout inside the 128-rounded array (tests/test_flash_attn.py:411-463), so sign patterns are directly comparable;
+    and with identical masks the outputs and gradients of the two kernels agree like two bf16 kernels do."""
+    from flash_attention_b200 import flash_attn_2_cuda as op
+    from tests.util import load_reference_fa2
+
+    real = load_reference_fa2()
+    q, k, v = make_qkv(b, sq, sk, h, hk, d, torch.bfloat16)
+    do = torch.randn(b, sq, h, d, device="cuda", dtype=torch.bfloat16)
+    scale = d ** -0.5
+    res = {}
+    for name, mod in (("ref", real), ("ours", op)):
+        torch.cuda.manual_seed(4321)   # same (seed, offset) for both
+        out, lse, s_dmask, rng = mod.fwd(q, k, v, None, None, p, scale, causal, -1, -1, 0.0, True, None)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        mod.bwd(do, q, k, v, out, lse, dq, dk, dv, None, p, scale, causal, -1, -1, 0.0, False, None, rng)
+        res[name] = (out, s_dmask[:, :, :sq, :sk].float(), rng.clone(), dq, dk, dv)
+    assert torch.equal(res["ref"][2], res["ours"][2])   # rng_state (seed, offset) as returned
+    pref, _ = _probs(q, k, causal, (-1, -1))
+    nz = (pref > 1e-4).cuda()   # entries whose probability survives fp16/bf16 storage in both kernels (sign is meaningful)
+    ref_keep, our_keep = res["ref"][1] >= 0, res["ours"][1] >= 0
+    assert nz.float().mean().item() > 0.05
+    assert torch.equal(ref_keep[nz], our_keep[nz]), "dropped elements differ from the reference kernels'"
+    frac = 1.0 - our_keep[nz].float().mean().item()
+    assert abs(frac - p) < 0.03, frac
+    for name, i, tol in (("out", 0, 2.0 ** -6), ("dq", 3, 2.0 ** -5), ("dk", 4, 2.0 ** -5), ("dv", 5, 2.0 ** -5)):
+        a, r = res["ours"][i].float(), res["ref"][i].float()
+        assert (a - r).abs().max().item() <= tol * max(1.0, r.abs().max().item()), name

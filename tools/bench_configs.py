@@ -82,5 +82,25 @@ for ns in ((0,) if which != "ours" else (0, 1, 2, 4)):
     byts = 2 * b * kv * hk * d * 2
     res.append(dict(cfg=f"C5 decode b64 sq1 h32/4 d128 kv65536 paged256 num_splits={ns}", ms=ms, gbps=byts / ms / 1e6,
                     frac_hbm_6572=byts / ms / 1e6 / 6572.2))
+# ragged varlen (packed, causal): 32k tokens in sequences from 8192 down to 1 token -- exercises the persistent kernels'
+# work-list scheduling (a max_seqlen grid would launch 24 x 64 m-blocks per head for 246 that exist)
+lens = [8192, 4096, 4096, 2048, 2048, 2048, 1024, 1024, 1024, 1024, 512, 512, 512, 512, 300, 300, 211, 173, 128, 64, 64, 33, 17, 1]
+cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+tot = sum(lens)
+qv, kv_, vv = (rnd(tot, 16, 128).requires_grad_(True) for _ in range(3))
+dov = rnd(tot, 16, 128)
+flv = sum(4 * 16 * (l * (l + 1) // 2) * 128 for l in lens)   # causal pairs per sequence
+
+
+def fbv():
+    o = fa.flash_attn_varlen_func(qv, kv_, vv, cu, cu, max(lens), max(lens), causal=True)
+    o.backward(dov)
+    qv.grad = kv_.grad = vv.grad = None
+
+
+ms = timeit(lambda: fa.flash_attn_varlen_func(qv, kv_, vv, cu, cu, max(lens), max(lens), causal=True))
+res.append(dict(cfg="ragged varlen causal fwd, 24 sequences 1..8192 tokens (32k total) h16 d128", ms=ms, tflops=flv / ms / 1e9))
+ms = timeit(fbv, n=5)
+res.append(dict(cfg="ragged varlen causal fwd+bwd, 24 sequences 1..8192 tokens (32k total) h16 d128", ms=ms, tflops=3.5 * flv / ms / 1e9))
 for r in res:
     print(json.dumps(r), flush=True)
