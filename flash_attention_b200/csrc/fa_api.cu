@@ -599,6 +599,10 @@ size_t fa_b200_sizeof_append_args(void) { return sizeof(fa_b200_append_args); }
 int fa_b200_debug_read_fwd_ts(unsigned long long* out, int n) {
   return cudaMemcpyFromSymbol(out, fa::g_fwd_ts, size_t(n) * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
 }
+int fa_b200_debug_read_fwd_items(unsigned long long* ts, unsigned int* sm) {
+  if (cudaMemcpyFromSymbol(ts, fa::g_fwd_item_ts, sizeof(unsigned long long) * 192 * 64 * 2) != cudaSuccess) return 1;
+  return cudaMemcpyFromSymbol(sm, fa::g_fwd_item_sm, sizeof(unsigned int) * 192) == cudaSuccess ? 0 : 1;
+}
 #endif
 int fa_b200_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t height,
                            int32_t kind, fa_b200_stream_t stream) {

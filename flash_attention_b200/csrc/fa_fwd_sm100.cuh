@@ -104,7 +104,7 @@ struct FwdCfg {
   static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
   static constexpr int kSmemQ = kTiles * kTileBytes;
   static constexpr int kSmemKV = kStages * kTileBytes;
-  static constexpr int kNumBars = 2 + 2 * kStages + 13;   // + q_empty[2], o_free[2] of the persistent loop
+  static constexpr int kNumBars = 2 + 2 * kStages + 14;   // + q_empty[2], o_free[2], v_start of the persistent loop
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");  // hd256 (1 tile, 194 KB) runs one CTA per SM
 };
@@ -141,8 +141,21 @@ __device__ unsigned long long g_fwd_ts[16 * 16];   // [iteration - 8][event]
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it >= 8 && it < 24)                   \
       g_fwd_ts[(it - 8) * 16 + (ev)] = clock64();                                                      \
   } while (0)
+// per item: globaltimer at the softmax warpgroup's entry into / exit from each work item, per CTA, + the SM id
+__device__ unsigned long long g_fwd_item_ts[192 * 64 * 2];
+__device__ unsigned int g_fwd_item_sm[192];
+#define FITEM(slot_)                                                                                  \
+  do {                                                                                                \
+    if (tile == 0 && wq == 0 && lane == 0 && blockIdx.x < 192 && r < 64) {                             \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      g_fwd_item_ts[(blockIdx.x * 64 + r) * 2 + (slot_)] = t_;                                         \
+      if (r == 0) { unsigned int sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_fwd_item_sm[blockIdx.x] = sm_; } \
+    }                                                                                                 \
+  } while (0)
 #else
 #define FTS(ev) do {} while (0)
+#define FITEM(slot_) do {} while (0)
 #endif
 
 #ifndef FA_FWD_POLY_PAIRS_FP8
@@ -333,6 +346,11 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   const uint32_t bar_v_clean = sBar + 8u * (10 + 2 * S);
   auto bar_q_empty = [&](int i) { return sBar + 8u * (11 + 2 * S + i); };   // every QK^T of the item has read Q_i
   auto bar_o_free = [&](int i) { return sBar + 8u * (13 + 2 * S + i); };    // the item's epilogue has read O_i out of TMEM
+  // the MMA thread has reached an item whose first V block has a ragged tail: the cleaner warp may look at that item's
+  // K/V slot.  (Without it the idle cleaner runs ahead of the pipeline by whole items, and a parity wait on a slot
+  // barrier that is a full ring revolution behind passes at once: it then zeroed rows of a LIVE block of the item
+  // still being computed -- a timing-dependent wrong result in split-KV decode with seqlen_k % 128 != 0.)
+  const uint32_t bar_v_start = sBar + 8u * (15 + 2 * S);
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSmemQ + Cfg::kSmemKV + 8 * Cfg::kNumBars);
@@ -361,6 +379,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         mbar_init(bar_kv_empty(s), 1);
       }
       mbar_init(bar_v_clean, 1);
+      mbar_init(bar_v_start, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -474,6 +493,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           first_pv[i] = true;
           if (act[i]) mbar_wait(bar_q_full(i), q_items[i] & 1, 200 + i);
         }
+        if (w.v_tail) mbar_arrive(bar_v_start);   // every MMA of the earlier items has been issued behind its kv_full waits
         // prologue: S_i = Q_i K_0^T for the tiles that start with the first streamed block
         mbar_wait(bar_kv_full(ring % S), (ring / S) & 1, 210);
         tc_fence_after();
@@ -541,7 +561,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   }
   // ================================================================== V-tail cleaner (otherwise idle warp)
   else if (warp == Cfg::kWarpClean) {
-    int ring = 0;
+    int ring = 0, vstart_cnt = 0;
     for (int r = 0; r < rounds; ++r) {
       const int L = item_of_round(r);
       FwdWork w;
@@ -551,6 +571,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         // exactly 0 there but 0 * NaN would poison O, so clear them before the first PV
         // (reference: Clear_OOB_MN on the V load, flash_fwd_kernel.h:254-262).
         const int rv = ring + 1;
+        mbar_wait(bar_v_start, vstart_cnt & 1, 251);
+        ++vstart_cnt;
         mbar_wait(bar_kv_full(rv % S), (rv / S) & 1, 250);
         const int valid = w.sk_b - (w.nblk_total - 1) * 128;
         const int nvec = (128 - valid) * 8;
@@ -580,6 +602,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       FwdWork w;
       if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w)) continue;
       if (tile >= w.ntiles) continue;
+      FITEM(0);
       const int bidb = w.bidb, split = w.split, slot = w.slot, hk_idx = w.hk_idx, shift = w.shift;
       const int row0 = w.row0, rows_total = w.rows_total, sk_b = w.sk_b, q_off = w.q_off;
       const int it_lo = w.it_lo(tile), it_hi = w.it_hi(tile);
@@ -852,52 +875,64 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         // (softmax.h:180, flash_fwd_kernel.h:544-582)
         lse_val = p.num_splits > 1 ? kNegInf : INFINITY;
       }
-      uint32_t o[kD] = {};   // the whole O row leaves TMEM first, so that the next item's P V may overwrite it (zeros if the
-                             // tile had no visible block: a maybe-uninitialised array would be demoted to local memory)
+      // The O row leaves TMEM before it is stored, so that the next item's P V may overwrite it while the stores drain
+      // (head dims above 128 in two halves of 128 columns: 256 live values would not fit the register budget).
+      constexpr int kH = kD > 128 ? 128 : kD;
       if (nblocks > 0) {
         mbar_wait(bar_o_full(tile), (blk - 1) & 1, 320 + tile);
         tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < kD; cc += 32) tmem_ld_x32(tO + cc, o + cc);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_o_free(tile));
       }
-      if (p.num_splits > 1) {
-        const int64_t prow = ((int64_t(split) * p.b + bidb) * p.h + head) * p.sq + qpos;
-        float* dst = p.o_accum + prow * kD;
-        if (row_valid) {
 #pragma unroll
-          for (int c = 0; c < kD; c += 4) {
-            float4 v4;
-            v4.x = __uint_as_float(o[c]) * inv;
-            v4.y = __uint_as_float(o[c + 1]) * inv;
-            v4.z = __uint_as_float(o[c + 2]) * inv;
-            v4.w = __uint_as_float(o[c + 3]) * inv;
-            *reinterpret_cast<float4*>(dst + c) = v4;
+      for (int h0 = 0; h0 < kD; h0 += kH) {
+        uint32_t o[kH] = {};   // zeros if the tile had no visible block (a maybe-uninitialised array would be demoted to local memory)
+        if (nblocks > 0) {
+#pragma unroll
+          for (int cc = 0; cc < kH; cc += 32) tmem_ld_x32(tO + h0 + cc, o + cc);
+          tmem_wait_ld();
+          if (h0 + kH == kD) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_o_free(tile));
           }
-          p.lse_accum[prow] = lse_val;
         }
-      } else {
-        OutT* dst = reinterpret_cast<OutT*>(p.o) + (p.cu_seqlens_q ? 0 : bidb * p.o_batch_stride) +
-                 int64_t(q_off + qpos) * p.o_row_stride + int64_t(head) * p.o_head_stride;
-        if (row_valid) {
+        if (p.num_splits > 1) {
+          const int64_t prow = ((int64_t(split) * p.b + bidb) * p.h + head) * p.sq + qpos;
+          float* dst = p.o_accum + prow * kD + h0;
+          if (row_valid) {
 #pragma unroll
-          for (int c = 0; c < kD; c += 8) {
-            if (c < p.d) {  // d is a multiple of 8
-              uint4 v4;
-              v4.x = Elt<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
-              v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
-              v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
-              v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
-              *reinterpret_cast<uint4*>(dst + c) = v4;
+            for (int c = 0; c < kH; c += 4) {
+              float4 v4;
+              v4.x = __uint_as_float(o[c]) * inv;
+              v4.y = __uint_as_float(o[c + 1]) * inv;
+              v4.z = __uint_as_float(o[c + 2]) * inv;
+              v4.w = __uint_as_float(o[c + 3]) * inv;
+              *reinterpret_cast<float4*>(dst + c) = v4;
+            }
+            if (h0 == 0) p.lse_accum[prow] = lse_val;
+          }
+        } else {
+          OutT* dst = reinterpret_cast<OutT*>(p.o) + (p.cu_seqlens_q ? 0 : bidb * p.o_batch_stride) +
+                   int64_t(q_off + qpos) * p.o_row_stride + int64_t(head) * p.o_head_stride + h0;
+          if (row_valid) {
+#pragma unroll
+            for (int c = 0; c < kH; c += 8) {
+              if (h0 + c < p.d) {  // d is a multiple of 8
+                uint4 v4;
+                v4.x = Elt<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+                v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+                v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+                v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+                *reinterpret_cast<uint4*>(dst + c) = v4;
+              }
+            }
+            if (h0 == 0) {
+              if (p.cu_seqlens_q) p.lse[int64_t(head) * p.total_q + q_off + qpos] = lse_val;
+              else p.lse[(int64_t(bidb) * p.h + head) * p.sq + qpos] = lse_val;
             }
           }
-          if (p.cu_seqlens_q) p.lse[int64_t(head) * p.total_q + q_off + qpos] = lse_val;
-          else p.lse[(int64_t(bidb) * p.h + head) * p.sq + qpos] = lse_val;
         }
       }
+      FITEM(1);
     }
   }
 
