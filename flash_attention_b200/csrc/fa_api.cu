@@ -162,6 +162,8 @@ struct FwdPlan {
   int has_left, has_right, wl, wr;
   int dropout;
   size_t ws_bytes;
+  size_t sched_off;   // byte offset of the dynamic scheduler's work counter inside the workspace ...
+  size_t sched_bytes; // ... and its size (0: none requested); the last sched_bytes of ws_bytes, optional for the caller
 };
 
 static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
@@ -279,6 +281,17 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   }
   // packed varlen: the (b + 1)-entry m-block prefix sum the persistent kernel enumerates its work items with
   if (a.cu_seqlens_q) pl->ws_bytes = ((size_t(a.b) + 1) * sizeof(int) + 255) & ~size_t(255);
+  // work counter of the dynamic scheduler: asked for when there can be more work items than resident CTAs (a B200 has
+  // 148 SMs; the launch decides with the real SM count and falls back to the static deal if the caller gave no scratch)
+  pl->sched_off = pl->sched_bytes = 0;
+  {
+    const int64_t items = int64_t(pl->num_m_blocks) * (a.h / pl->gp) * a.b * splits;
+    if (items > 148 || a.cu_seqlens_q) {
+      pl->sched_off = pl->ws_bytes;
+      pl->sched_bytes = 256;
+      pl->ws_bytes += pl->sched_bytes;
+    }
+  }
   return 0;
 }
 
@@ -309,7 +322,8 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   FwdPlan pl;
   if (!a.q || !a.k || !a.v || !a.out || !a.softmax_lse) return set_error("q, k, v, out, softmax_lse must be non-null");
   if (int rc = plan_fwd(a, mode, &pl)) return rc;
-  if (pl.ws_bytes > 0 && (!a.workspace || a.workspace_bytes < pl.ws_bytes))
+  const size_t ws_required = pl.ws_bytes - pl.sched_bytes;   // the scheduler's counter is optional
+  if (ws_required > 0 && (!a.workspace || a.workspace_bytes < ws_required))
     return set_error(pl.num_splits > 1 ? "workspace too small for split-KV (query fa_b200_fwd_workspace_bytes)"
                                        : "workspace too small for the varlen work list (query fa_b200_fwd_workspace_bytes)");
   if (a.seqlen_q == 0 || (mode == kVarlen && a.total_q == 0)) return 0;
@@ -408,9 +422,13 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   int sms = num_sms() - std::max(0, a.sm_margin);
   if (sms < 1) sms = 1;
   int64_t ctas = int64_t(sms) * ctas_per_sm;
+  static const bool sched_dynamic = [] { const char* e = getenv("FA_B200_SCHED_DYNAMIC"); return e ? atoi(e) != 0 : true; }();
+  int* sched_counter = (sched_dynamic && pl.sched_bytes && a.workspace && a.workspace_bytes >= pl.sched_off + sizeof(int))
+                           ? reinterpret_cast<int*>(static_cast<char*>(a.workspace) + pl.sched_off) : nullptr;
   if (a.cu_seqlens_q) {
     int* prefix = reinterpret_cast<int*>(a.workspace);
-    fa_fwd_varlen_prepare<<<1, 256, 0, stream>>>(a.cu_seqlens_q, a.seqused_q, a.b, gp, 128 * pl.tiles, prefix);
+    if (sched_counter) kp.sched_counter = sched_counter;   // zeroed by the prepare kernel
+    fa_fwd_varlen_prepare<<<1, 256, 0, stream>>>(a.cu_seqlens_q, a.seqused_q, a.b, gp, 128 * pl.tiles, prefix, sched_counter);
     g_launch_count++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(std::string("fa_fwd_varlen_prepare launch: ") + cudaGetErrorString(e));
@@ -418,6 +436,11 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     ctas = std::min<int64_t>(ctas, std::max<int64_t>(1, total_items));   // upper bound: max_seqlen m-blocks per batch
   } else {
     ctas = std::min<int64_t>(ctas, total_items);
+    if (sched_counter && total_items > ctas) {
+      if (cudaError_t e = cudaMemsetAsync(sched_counter, 0, sizeof(int), stream); e != cudaSuccess)
+        return set_error(std::string("cudaMemsetAsync(work counter): ") + cudaGetErrorString(e));
+      kp.sched_counter = sched_counter;
+    }
   }
   dim3 grid(unsigned(ctas), 1, 1);
   int rc;

@@ -70,7 +70,7 @@ struct Bwd2Cfg {
   static constexpr int kSDX = kSDQ + 16384;      // export staging: the dS^T rows owed to the peer (128 keys x 64 queries)
   static constexpr int kSStat = kSDX + 16384;    // lse_log2[2][128], dpsum[2][128]
   static constexpr int kSBar = kSStat + 2048;
-  static constexpr int kNumBars = 29;
+  static constexpr int kNumBars = 33;   // 29..30 SCHED_FULL[2], 31..32 SCHED_EMPTY[2] (dynamic scheduler)
   static constexpr int kSmemBytes = kSBar + 8 * kNumBars + 16;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -123,8 +123,58 @@ __device__ __forceinline__ bool bwd2_decode_work(const BwdKernelParams& p, int L
   return true;
 }
 
-// PERSISTENT: the grid is one CTA pair (cluster) per two SMs; every pair loops over work items (bwd2_decode_work), dealt
-// out in snake order (round r: cluster c takes item r*G + c, or r*G + G-1-c on odd rounds).  Barrier phases, the Q / dO
+
+// Work-item sequence of one role of the persistent pair kernel (cf. FwdSched).  Dynamic mode: cluster c starts with item c;
+// the LEADER CTA's TMA thread draws the following ones from the global counter and hands each to both CTAs with a 4-byte
+// st.async into a two-slot ring (SCHED_FULL counts its tx-bytes; each CTA's own TMA thread arms the barrier); every role of
+// both CTAs acknowledges on the leader's SCHED_EMPTY.  Items come out of the counter in list order, so an item only ever
+// waits (deterministic dQ chains) for items that were started before it.
+struct Bwd2Sched {
+  int G, cl, total, rounds, k;
+  uint32_t full0, empty0, item_addr;   // this CTA's shared::cta addresses
+  uint32_t empty0_leader;              // shared::cluster address of the leader's SCHED_EMPTY[0]
+  bool dyn;
+  __device__ __forceinline__ int static_item(int r) const { return r * G + ((r & 1) ? (G - 1 - cl) : cl); }
+  __device__ __forceinline__ int first() {
+    k = 0;
+    return cl < total ? cl : -1;
+  }
+  __device__ __forceinline__ int next_static() {
+    if (k >= rounds) return -1;
+    const int L = static_item(k);
+    return L < total ? L : -1;
+  }
+  // every role except the leader's TMA thread.  arm: the caller is the (peer) CTA's TMA thread, which arms SCHED_FULL
+  __device__ __forceinline__ int next(bool whole_warp, int lane, bool arm = false) {
+    ++k;
+    if (!dyn) return next_static();
+    const int j = k - 1;
+    const uint32_t s = uint32_t(j & 1);
+    if (arm) mbar_arrive_expect_tx(full0 + 8u * s, 4);
+    mbar_wait(full0 + 8u * s, (j >> 1) & 1, 700);
+    int L;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(L) : "r"(item_addr + 4u * s) : "memory");
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) mbar_arrive_cluster(empty0_leader + 8u * s);
+    return L < total ? L : -1;
+  }
+  __device__ __forceinline__ int draw(int* counter) const { return G + atomicAdd(counter, 1); }
+  // the leader's TMA thread
+  __device__ __forceinline__ int publish(int L) {
+    const int j = k++;
+    const uint32_t s = uint32_t(j & 1);
+    mbar_wait(empty0 + 8u * s, ((j >> 1) & 1) ^ 1, 701);
+    mbar_arrive_expect_tx(full0 + 8u * s, 4);
+#pragma unroll
+    for (uint32_t rk = 0; rk < 2; ++rk)
+      st_async_b32(mapa_rank(item_addr + 4u * s, rk), uint32_t(L), mapa_rank(full0 + 8u * s, rk));
+    return L < total ? L : -1;
+  }
+};
+
+// PERSISTENT: the grid is one CTA pair (cluster) per two SMs; every pair loops over work items (bwd2_decode_work), drawn
+// dynamically from a global counter (Bwd2Sched) or, without one, dealt out in snake order (round r: cluster c takes item
+// r*G + c, or r*G + G-1-c on odd rounds).  Barrier phases, the Q / dO
 // stages and TMEM stay live across items; what an item needs from its predecessor is tracked by two extra barriers
 // (ACC_FREE: dV / dK accumulators read out by both CTAs' epilogues; STAGE_FREE: the epilogue's dV / dK staging -- the dS^T and
 // K^T buffers, idle at the end of an item -- has been read by its TMA stores in both CTAs).  K / V are free as soon as the
@@ -139,7 +189,6 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   const int G = int(gridDim.x >> 1), cl = int(blockIdx.x >> 1);
   const int total_items = p.total_items;
   const int rounds = (total_items + G - 1) / G;
-  auto item_of_round = [&](int r) { return r * G + ((r & 1) ? (G - 1 - cl) : cl); };
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -153,10 +202,16 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
   // F_*: "operand landed" barriers, live in the LEADER (rank 0) and collect the TMA bytes of both CTAs
   // E_*: "operand consumed" barriers, one per CTA, signalled by multicast tcgen05.commit
   enum { F_KV = 0, F_QB = 1, F_DOB = 2, F_DOG = 3, F_QG = 4, E_QB = 5, E_DOB = 6, E_DOG = 7, E_QG = 8, F_ST0 = 9,
-         F_ST1 = 10, S_F = 11, DP_F = 12, P_F = 13, DS_F = 14, DQ_F = 15, DQ_E = 16, DKV_F = 17, DS_IN = 18, DS_PEER = 19, T_DV = 20, T_S = 21, T_DK = 22, T_DQ = 23, T_DP = 24, S_RD = 25, ACC_FREE = 26, STAGE_FREE = 27, F_KT = 28 };
+         F_ST1 = 10, S_F = 11, DP_F = 12, P_F = 13, DS_F = 14, DQ_F = 15, DQ_E = 16, DKV_F = 17, DS_IN = 18, DS_PEER = 19, T_DV = 20, T_S = 21, T_DK = 22, T_DQ = 23, T_DP = 24, S_RD = 25, ACC_FREE = 26, STAGE_FREE = 27, F_KT = 28, SCHED_FULL0 = 29, SCHED_EMPTY0 = 31 };
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSBar + 8 * Cfg::kNumBars);
+
+  Bwd2Sched sched;
+  sched.G = G; sched.cl = cl; sched.total = total_items; sched.rounds = rounds; sched.k = 0;
+  sched.full0 = bar(SCHED_FULL0); sched.empty0 = bar(SCHED_EMPTY0); sched.item_addr = sTmemPtr + 8u;
+  sched.empty0_leader = mapa_rank(bar(SCHED_EMPTY0), 0);
+  sched.dyn = p.sched_counter != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TSX(0);
@@ -196,6 +251,10 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       mbar_init(bar(STAGE_FREE), 2); // per CTA: the dV / dK staging (the dS^T and K^T buffers, idle at the end of an item) of BOTH
                                      // CTAs has been read by the epilogue's TMA stores (one arrive from each CTA's epilogue thread)
       mbar_init(bar(F_KT), 1);       // leader: the K^T panels of both CTAs have landed (loaded after STAGE_FREE, needed by dQ only)
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar(SCHED_FULL0 + i), 1);    // armed by this CTA's TMA thread (+ 4 tx-bytes: the item index)
+        mbar_init(bar(SCHED_EMPTY0 + i), 27);  // leader only: MMA thread + 4 drain + 8 compute warps; peer: + TMA and relay threads
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -220,10 +279,17 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         const int dcol = 64 * int(rank);
         int git = 0;      // tiles processed so far by this pair, over all its items: phase of the per-tile barriers
         int kitem = 0;    // items with work processed so far: phase of F_KV / F_KT / DKV_F / STAGE_FREE
-        for (int r = 0; r < rounds; ++r) {
-          const int L = item_of_round(r);
+        int nxt = -1;
+        bool drawn = false;
+        auto advance = [&]() -> int {
+          if (!sched.dyn || rank != 0) return sched.next(false, 0, /*arm=*/true);
+          if (!drawn) nxt = sched.draw(p.sched_counter);
+          drawn = false;
+          return sched.publish(nxt);
+        };
+        for (int L = sched.first(); L >= 0; L = advance()) {
           Bwd2Work w;
-          if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+          if (!bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
           const int bk = p.cu_seqlens_k ? 0 : w.bidb, bq = p.cu_seqlens_q ? 0 : w.bidb;
           const int key0 = w.pkey0 + 128 * int(rank);
           // this pair's K / V tiles are free once the previous item's last MMA is done (multicast commit)
@@ -235,6 +301,10 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
             tma_load_4d_pair(sV + pn * 16384, &p.tm_v, fKV, pn * 64, w.k_off + key0, w.hk, bk);
           }
           for (int it = 0; it < w.n_iter; ++it, ++git) {
+            if (sched.dyn && rank == 0 && !drawn && it + 2 >= w.n_iter) {   // the next item is needed two tiles from now
+              nxt = sched.draw(p.sched_counter);
+              drawn = true;
+            }
             // (first tile: the K^T panel is loaded behind the Q rows below.  It doubles as the dK staging of the previous
             // item's epilogue, so it waits for those TMA stores in both CTAs; dQ, its first consumer, is a tile's work away)
             const int hq = w.hk * p.g + it / w.n_m;
@@ -280,7 +350,7 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
       if (rank == 0 && lane == 0 && blockIdx.x < 2) {   // completion times of the MMA groups (leader clock), first item only
         Bwd2Work w;
         const bool ts_on = true;
-        if (bwd2_decode_work(p, item_of_round(0), w)) {
+        if (bwd2_decode_work(p, sched.static_item(0), w)) {
           for (int it = 0; it < w.n_iter; ++it) {
             mbar_wait(bar(T_DV), it & 1, 800); TS(21);
             if (it + 1 < w.n_iter) { mbar_wait(bar(T_S), it & 1, 801); TS(22); }
@@ -332,10 +402,11 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         // critical path (it only has to be drained before S^T(n+2) is issued).  Tiles are numbered `git` across ALL items of
         // this pair (barrier phases continue); an item's first S^T / dP^T are issued while its predecessor's epilogue runs.
         int git = 0, kitem = 0;
-        for (int r = 0; r < rounds; ++r) {
-          const int L = item_of_round(r);
+        int r = -1;
+        for (int L = sched.first(); L >= 0; L = sched.next(false, 0)) {
+          ++r;
           Bwd2Work w;
-          if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+          if (!bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
           const bool ts_on = FA_BWD2_TS && r == 0 && blockIdx.x < 2;
           (void)ts_on;
           mbar_wait(bar(F_KV), kitem & 1, 500);
@@ -428,10 +499,9 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
         // relay: tell the leader when this CTA's dS^T tile (local stores + the peer's bulk copy) is complete
         const uint32_t peer_bar = mapa_rank(bar(DS_PEER), 0);
         int git = 0;
-        for (int r = 0; r < rounds; ++r) {
-          const int L = item_of_round(r);
+        for (int L = sched.first(); L >= 0; L = sched.next(false, 0)) {
           Bwd2Work w;
-          if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+          if (!bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
           for (int it = 0; it < w.n_iter; ++it, ++git) {
             mbar_wait(bar(DS_IN), git & 1, 520);
             fence_proxy_async();
@@ -452,10 +522,11 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     const bool leader = (warp == 8 && lane == 0);
     const uint32_t dqe = mapa_rank(bar(DQ_E), 0);
     int git = 0;
-    for (int r = 0; r < rounds; ++r) {
-    const int L = item_of_round(r);
+    int r = -1;
+    for (int L = sched.first(); L >= 0; L = sched.next(true, lane)) {
+    ++r;
     Bwd2Work w;
-    if (L >= total_items || !bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
+    if (!bwd2_decode_work(p, L, w) || w.n_iter == 0) continue;
     const bool ts_on = FA_BWD2_TS && r == 0 && blockIdx.x < 2;
     (void)ts_on;
     const int bidb = w.bidb, pair = w.pair, shift = w.shift;
@@ -545,10 +616,11 @@ fa_bwd2_kernel(const __grid_constant__ BwdKernelParams p) {
     }
     const uint32_t acc_free = mapa_rank(bar(ACC_FREE), 0);
     int git = 0, kitem = 0;
-    for (int rr = 0; rr < rounds; ++rr) {
-    const int L = item_of_round(rr);
+    int rr = -1;
+    for (int L = sched.first(); L >= 0; L = sched.next(true, lane)) {
+    ++rr;
     Bwd2Work w;
-    if (L >= total_items || !bwd2_decode_work(p, L, w)) continue;
+    if (!bwd2_decode_work(p, L, w)) continue;
     const bool ts_on = FA_BWD2_TS && rr == 0 && blockIdx.x < 2;
     (void)ts_on;
     const int n_iter = w.n_iter, n_m = w.n_m, m_min = w.m_min, hk = w.hk, bidb = w.bidb, shift = w.shift, sk_b = w.sk_b;

@@ -21,7 +21,7 @@ struct BwdPlan {
   int kD, sq_r;
   int64_t ws_rows_head;   // packed varlen layout: rows per head (0 = dense layout)
   int has_left, has_right, wl, wr;
-  size_t off_lse, off_dps, off_dq, off_sem, total;
+  size_t off_lse, off_dps, off_dq, off_sem, off_sched, total;
 };
 
 // head dims 129..256 run fa_bwd256_kernel (fa_bwd256_sm100.cuh); FA_B200_BWD_HD256=0 restores the round-1 behaviour
@@ -60,7 +60,8 @@ static int plan_bwd(const fa_b200_bwd_args& a, bool varlen, BwdPlan* pl) {
   pl->off_dq = pl->off_dps + align256(stat);
   pl->off_sem = pl->off_dq + align256(stat * pl->kD);   // deterministic mode: one counter per (b, h, query block),
   const size_t sem = size_t(a.b) * a.h * (pl->sq_r / 128) * sizeof(int);   // semaphores stay (b, h, query block)
-  pl->total = pl->off_sem + align256(sem * (pl->kD == 256 ? 4 : 2));   // placed right behind dq_accum so one
+  pl->off_sched = pl->off_sem + align256(sem * (pl->kD == 256 ? 4 : 2));   // work counter of the pair kernel's scheduler
+  pl->total = pl->off_sched + 256;                                      // semaphores placed right behind dq_accum so one
                           // memset clears both (x2: the CTA-pair kernel orders each query half separately; x4: the
                           // head-dim 256 kernel has one chain per 64-query tile and output half)
   return 0;
@@ -148,7 +149,8 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
     fa_bwd_preprocess<T><<<grid, 256, 0, stream>>>(
         reinterpret_cast<const T*>(a.out), reinterpret_cast<const T*>(a.dout), a.softmax_lse, dpsum, lse_log2, a.softmax_d,
         a.o_batch_stride, a.o_row_stride, a.o_head_stride, a.do_batch_stride, a.do_row_stride, a.do_head_stride,
-        a.cu_seqlens_q, a.b, a.h, a.seqlen_q, sq_r, a.d, a.total_q, clear_rows, kD, pl.ws_rows_head);
+        a.cu_seqlens_q, a.b, a.h, a.seqlen_q, sq_r, a.d, a.total_q, clear_rows, kD, pl.ws_rows_head,
+        reinterpret_cast<int*>(ws + pl.off_sched));
     g_launch_count++;
     if ((e = cudaGetLastError()) != cudaSuccess) return set_error(std::string("fa_bwd_preprocess launch: ") + cudaGetErrorString(e));
   }
@@ -236,6 +238,11 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
       const int64_t total = int64_t(kp.num_pairs) * hz_total;
       if (total > INT32_MAX) return set_error("too many work items");
       kp.total_items = int(total);
+      static const bool sched_dynamic = [] { const char* e = getenv("FA_B200_SCHED_DYNAMIC"); return e ? atoi(e) != 0 : true; }();
+      {
+        const int sms = std::max(2, num_sms() - std::max(0, a.sm_margin));
+        if (sched_dynamic && total > sms / 2) kp.sched_counter = reinterpret_cast<int*>(ws + pl.off_sched);
+      }
       rc = a.p_dropout > 0.f ? launch_bwd_pair<T, false, true>(kp, grid, stream, a.sm_margin)
          : a.softcap > 0.f ? launch_bwd_pair<T, true, false>(kp, grid, stream, a.sm_margin)
                            : launch_bwd_pair<T, false, false>(kp, grid, stream, a.sm_margin);

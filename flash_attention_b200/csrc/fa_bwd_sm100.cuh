@@ -59,6 +59,7 @@ struct BwdKernelParams {
   float softcap_pre;
   int sched_lpt;              // (single-CTA kernel) key block index is the slowest grid dimension: heavy (masked) work first
   int num_pairs, sched_group, total_items;   // persistent CTA-pair kernel (fa_bwd2_sm100.cuh): work-item enumeration
+  int* sched_counter;                        // its dynamic scheduler's work counter (zeroed by fa_bwd_preprocess), or nullptr
   DropoutParams drop;         // kDropout kernels only: the forward's rng_state and p_dropout
   const uint64_t* rng_state;  // device copy of {seed, offset}; overrides drop.seed/off when non-null
   float* dq_accum;            // fa_bwd256_kernel only (adds its dQ partials with red.global instead of TMA): (b, h, sq_r, 256)
@@ -121,9 +122,11 @@ __global__ void __launch_bounds__(256) fa_bwd_preprocess(const T* __restrict__ o
                                                          int64_t o_bs, int64_t o_rs, int64_t o_hs, int64_t do_bs,
                                                          int64_t do_rs, int64_t do_hs, const int* __restrict__ cu_q,
                                                          int b, int h, int sq, int sq_r, int d, int total_q,
-                                                         float* __restrict__ dq_accum_rows, int kD, int64_t ws_head_pitch) {
+                                                         float* __restrict__ dq_accum_rows, int kD, int64_t ws_head_pitch,
+                                                         int* __restrict__ sched_counter) {
   constexpr int kRows = 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (sched_counter && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *sched_counter = 0;
   const int row0 = (blockIdx.x * 8 + warp) * kRows;  // in [0, sq_r)
   const int head = blockIdx.y, bidb = blockIdx.z;
   if (row0 >= sq_r) return;

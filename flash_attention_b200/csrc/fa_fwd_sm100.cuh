@@ -3,9 +3,11 @@
 // PERSISTENT: the grid is one CTA per SM (two for the 1-tile configuration); every CTA loops over work items.  A work
 // item is up to two 128-row query tiles ("tile 0/1", 256 packed rows) of one (batch, head-slot, split); its K/V blocks
 // stream right-to-left (masked blocks first, like the reference: csrc/flash_attn/src/flash_fwd_kernel.h:138-140,274).
-// Item order (fwd_decode_work): heavy (causal) m-blocks first inside groups of heads whose K/V fit L2 together, dealt to
-// the CTAs in snake order (round r: CTA c takes item r*G + c, or r*G + G-1-c on odd rounds) so that every CTA pairs a heavy
-// with a light item (cf. the reference's LPT + L2 swizzle scheduler, flash_attn/cute/tile_scheduler.py:458-530); packed
+// Item order (fwd_decode_work): heavy (causal) m-blocks first inside groups of heads whose K/V fit L2 together (cf. the
+// reference's LPT + L2 swizzle scheduler, flash_attn/cute/tile_scheduler.py:458-530).  With more items than CTAs they are
+// drawn DYNAMICALLY from a global counter (struct FwdSched; cf. hopper/tile_scheduler.hpp DynamicPersistentTileScheduler);
+// otherwise, or without scratch memory for the counter, dealt statically in snake order (round r: CTA c takes item
+// r*G + c, or r*G + G-1-c on odd rounds).  Packed
 // varlen batches are enumerated through a per-batch m-block prefix sum written by fa_fwd_varlen_prepare (cf.
 // hopper/flash_prepare_scheduler.cu:43-215) instead of a max_seqlen grid with early exits.  Barrier phases, the K/V ring
 // and TMEM stay live across items: the next item's Q / K loads and first S = QK^T run under the current item's epilogue.
@@ -73,6 +75,8 @@ struct FwdKernelParams {
   int num_m_blocks;         // dense: m-blocks per (batch, head slot); varlen: upper bound (max_seqlen_q)
   int total_items;          // dense: num_m_blocks * head slots * batch * splits; varlen: read from varlen_prefix[b]
   const int* varlen_prefix; // packed varlen: exclusive prefix sum of per-batch m-block counts, (b + 1) ints, else nullptr
+  int* sched_counter;       // dynamic scheduling: zeroed before the launch; CTA c starts with item c and then takes item
+                            // gridDim.x + atomicAdd(sched_counter, 1) until the list is exhausted.  nullptr: static rounds
   float scale;              // effective softmax scale (softcap if softcap > 0)
   float scale_log2;         // scale * log2(e)
   float softcap_pre;        // softmax_scale / softcap, 0 = off
@@ -104,7 +108,7 @@ struct FwdCfg {
   static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
   static constexpr int kSmemQ = kTiles * kTileBytes;
   static constexpr int kSmemKV = kStages * kTileBytes;
-  static constexpr int kNumBars = 2 + 2 * kStages + 14;   // + q_empty[2], o_free[2], v_start of the persistent loop
+  static constexpr int kNumBars = 2 + 2 * kStages + 18;   // + q_empty[2], o_free[2], v_start, sched_full[2], sched_empty[2]
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");  // hd256 (1 tile, 194 KB) runs one CTA per SM
 };
@@ -284,9 +288,11 @@ __device__ __forceinline__ bool fwd_decode_work(const FwdKernelParams& p, int L,
 // per-batch m-block counts of a packed varlen batch -> exclusive prefix sum (b + 1 ints): the persistent kernel
 // enumerates exactly the m-blocks that exist (reference: hopper/flash_prepare_scheduler.cu:43-215)
 static __global__ void __launch_bounds__(256) fa_fwd_varlen_prepare(const int* __restrict__ cu_seqlens_q, const int* __restrict__ seqused_q,
-                                                            int b, int gp, int rows_per_cta, int* __restrict__ prefix) {
+                                                            int b, int gp, int rows_per_cta, int* __restrict__ prefix,
+                                                            int* __restrict__ sched_counter) {
   __shared__ int part[256];
   const int t = threadIdx.x;
+  if (t == 0 && sched_counter) *sched_counter = 0;
   const int per = (b + 255) / 256;
   int sum = 0;
   for (int i = t * per; i < b && i < (t + 1) * per; ++i) {
@@ -311,6 +317,49 @@ static __global__ void __launch_bounds__(256) fa_fwd_varlen_prepare(const int* _
   }
 }
 
+
+// Work-item sequence of one role of the persistent kernel.  Static mode (no counter): round r -> item r*G + c (snake
+// order on odd rounds).  Dynamic mode: item c first, then whatever the CTA's TMA thread draws from the global counter;
+// it publishes each draw through a two-slot shared-memory ring (sched_full / sched_empty mbarriers) that every other
+// role reads in step.  Items are ordered heavy-first inside L2-sized head groups (fwd_decode_work), so a dynamic draw is
+// longest-processing-time-first list scheduling: the static deal lost 8 % of a causal 8k forward to imbalance
+// (profiles/r02_fwd_item_timeline.log).
+struct FwdSched {
+  int G, cta, total, rounds, k;
+  uint32_t bar_full0, bar_empty0, item_addr;   // shared-memory addresses (barriers 8 bytes apart, items 4 bytes apart)
+  bool dyn;
+  __device__ __forceinline__ int static_item(int r) const { return r * G + ((r & 1) ? (G - 1 - cta) : cta); }
+  __device__ __forceinline__ int first() {
+    k = 0;
+    return cta < total ? cta : -1;
+  }
+  // consumer roles; `lanes`: the whole warp calls (lane 0 signals after all lanes have read the slot)
+  __device__ __forceinline__ int next(bool whole_warp, int lane) {
+    ++k;
+    if (!dyn) {
+      if (k >= rounds) return -1;
+      const int L = static_item(k);
+      return L < total ? L : -1;
+    }
+    const int j = k - 1;
+    mbar_wait(bar_full0 + 8u * (j & 1), (j >> 1) & 1, 600);
+    int L;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(L) : "r"(item_addr + 4u * (j & 1)) : "memory");
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) mbar_arrive(bar_empty0 + 8u * (j & 1));
+    return L < total ? L : -1;
+  }
+  // TMA thread, dynamic mode: draw() may be called early (while the current item's last loads are being issued)
+  __device__ __forceinline__ int draw(int* counter) const { return G + atomicAdd(counter, 1); }
+  __device__ __forceinline__ int publish(int L) {   // returns the item to continue with (-1: none)
+    const int j = k++;
+    mbar_wait(bar_empty0 + 8u * (j & 1), ((j >> 1) & 1) ^ 1, 601);
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(item_addr + 4u * (j & 1)), "r"(L) : "memory");
+    mbar_arrive(bar_full0 + 8u * (j & 1));
+    return L < total ? L : -1;
+  }
+};
+
 template <typename T, int kD, int kTiles, bool kDropout = false>
 __global__ void __launch_bounds__((FwdCfg<kD, 2, kTiles>::kThreads), (FwdCfg<kD, 2, kTiles>::kCtasPerSm))
 fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
@@ -328,7 +377,6 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   const int G = int(gridDim.x), cta = int(blockIdx.x);
   const int total_items = p.varlen_prefix ? p.varlen_prefix[p.b] * (p.h / p.gp) : p.total_items;
   const int rounds = (total_items + G - 1) / G;
-  auto item_of_round = [&](int r) { return r * G + ((r & 1) ? (G - 1 - cta) : cta); };
 
   // ------------------------------------------------------------------ shared memory carve-up
   extern __shared__ uint8_t smem_raw[];
@@ -351,7 +399,12 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   // barrier that is a full ring revolution behind passes at once: it then zeroed rows of a LIVE block of the item
   // still being computed -- a timing-dependent wrong result in split-KV decode with seqlen_k % 128 != 0.)
   const uint32_t bar_v_start = sBar + 8u * (15 + 2 * S);
+  const uint32_t bar_sched_full0 = sBar + 8u * (16 + 2 * S), bar_sched_empty0 = sBar + 8u * (18 + 2 * S);
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
+  FwdSched sched;
+  sched.G = G; sched.cta = cta; sched.total = total_items; sched.rounds = rounds; sched.k = 0;
+  sched.bar_full0 = bar_sched_full0; sched.bar_empty0 = bar_sched_empty0; sched.item_addr = sTmemPtr + 8u;
+  sched.dyn = p.sched_counter != nullptr;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSmemQ + Cfg::kSmemKV + 8 * Cfg::kNumBars);
 
@@ -380,6 +433,10 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       }
       mbar_init(bar_v_clean, 1);
       mbar_init(bar_v_start, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_sched_full0 + 8u * i, 1);
+        mbar_init(bar_sched_empty0 + 8u * i, 2 + 4 * kTiles);   // MMA thread, cleaner warp, softmax warps
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -399,10 +456,17 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
     if (elect_one()) {
       int ring = 0;              // running K/V slot counter across items: K_it -> ring, V_it -> ring + 1
       int q_items[2] = {0, 0};   // items so far that used Q tile i
-      for (int r = 0; r < rounds; ++r) {
-        const int L = item_of_round(r);
+      int nxt = -1;
+      bool drawn = false;
+      auto advance = [&]() -> int {
+        if (!sched.dyn) return sched.next(false, 0);
+        if (!drawn) nxt = sched.draw(p.sched_counter);
+        drawn = false;
+        return sched.publish(nxt);
+      };
+      for (int L = sched.first(); L >= 0; L = advance()) {
         FwdWork w;
-        if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
+        if (!fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
         const int bq = p.cu_seqlens_q ? 0 : w.bidb;
 #pragma unroll
         for (int i = 0; i < kTiles; ++i) {
@@ -418,6 +482,10 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           }
         }
         for (int it = 0; it < w.nblocks; ++it) {
+          if (sched.dyn && !drawn && it + 2 >= w.nblocks) {   // the next item's index is needed two blocks from now
+            nxt = sched.draw(p.sched_counter);
+            drawn = true;
+          }
           const int j = w.n_max - 1 - it;
           int row = w.k_off + j * 128, c3 = p.cu_seqlens_k ? 0 : (p.cache_batch_idx ? p.cache_batch_idx[w.bidb] : w.bidb);
           if (p.page_size) {
@@ -480,10 +548,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       int ring = 0, vclean_cnt = 0;
       int q_items[2] = {0, 0};   // items so far in which tile i had work (Q_i loaded, O_i produced)
       int blk[2] = {0, 0};       // blocks so far processed by tile i: phase of s_full / p_full / o_full
-      for (int r = 0; r < rounds; ++r) {
-        const int L = item_of_round(r);
+      for (int L = sched.first(); L >= 0; L = sched.next(false, 0)) {
         FwdWork w;
-        if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
+        if (!fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
         const int it = 0;  // (FTS below refers to the first item's iterations only)
         (void)it;
         bool act[2], first_pv[2];
@@ -562,10 +629,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   // ================================================================== V-tail cleaner (otherwise idle warp)
   else if (warp == Cfg::kWarpClean) {
     int ring = 0, vstart_cnt = 0;
-    for (int r = 0; r < rounds; ++r) {
-      const int L = item_of_round(r);
+    for (int L = sched.first(); L >= 0; L = sched.next(true, lane)) {
       FwdWork w;
-      if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
+      if (!fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
       if (w.v_tail) {
         // Rows of the last V block beyond seqlen_k may hold garbage (kv-cache tail, next sequence): P is
         // exactly 0 there but 0 * NaN would poison O, so clear them before the first PV
@@ -597,10 +663,11 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
     const uint32_t tS = tmem_base + lane_sel + tile * 128;
     const uint32_t tO = tmem_base + lane_sel + kTiles * 128 + tile * kD;
     int blk = 0;   // blocks processed so far by this tile (phase of s_full / o_full)
-    for (int r = 0; r < rounds; ++r) {
-      const int L = item_of_round(r);
+    int r = -1;   // items seen by this CTA (debug / timeline hooks refer to the first one)
+    for (int L = sched.first(); L >= 0; L = sched.next(true, lane)) {
+      ++r;
       FwdWork w;
-      if (L >= total_items || !fwd_decode_work<kRowsPerCta, kTiles>(p, L, w)) continue;
+      if (!fwd_decode_work<kRowsPerCta, kTiles>(p, L, w)) continue;
       if (tile >= w.ntiles) continue;
       FITEM(0);
       const int bidb = w.bidb, split = w.split, slot = w.slot, hk_idx = w.hk_idx, shift = w.shift;

@@ -226,6 +226,12 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint
                ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar)
                : "memory");
 }
+// 4-byte variant (work-item hand-over of the persistent pair kernel's scheduler)
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(cluster_addr), "r"(v), "r"(cluster_bar)
+               : "memory");
+}
 __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)

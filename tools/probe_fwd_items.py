@@ -28,7 +28,7 @@ used = t[:, :, 1] > 0
 t0 = int(t[:, 0, 0].min())
 dur = (t[:, :, 1] - t[:, :, 0]).float() / 1e3
 n_items = used.sum(1)
-end = torch.stack([t[c, int(n_items[c]) - 1, 1] for c in range(G)]).float() - t0
+end = (torch.stack([t[c, int(n_items[c]) - 1, 1] for c in range(G)]) - t0).float()   # (subtract in int64: ns since boot)
 start = (t[:, 0, 0] - t0).float()
 print(f"causal={causal}: items per CTA {int(n_items.min())}..{int(n_items.max())}; kernel span {float(end.max()) / 1e3:.1f} us")
 print(f"first-item entry: min {float(start.min()) / 1e3:.2f} us max {float(start.max()) / 1e3:.2f} us")
