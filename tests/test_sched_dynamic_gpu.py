@@ -70,8 +70,12 @@ def test_backward_few_clusters(ops, b, sq, sk, h, hk, d, causal, window, ctas, d
     dout = torch.randn_like(q)
     kw = dict(is_causal=causal, window_size_left=window[0], window_size_right=window[1])
     out, lse, _, _ = ops.fwd(q, k, v, **kw)
-    g0 = ops.bwd(dout, q, k, v, out, lse, deterministic=deterministic, **kw)[:3]
-    g1 = ops.bwd(dout, q, k, v, out, lse, deterministic=deterministic, sm_margin=_margin(ctas), **kw)[:3]
+    def grads(sm_margin):   # FA3 convention: dq / dk / dv are written in place, the op returns softmax_d + scratch
+        g = [torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)]
+        ops.bwd(dout, q, k, v, out, lse, g[0], g[1], g[2], deterministic=deterministic, sm_margin=sm_margin, **kw)
+        return g
+
+    g0, g1 = grads(0), grads(_margin(ctas))
     assert torch.equal(g0[1], g1[1]) and torch.equal(g0[2], g1[2])   # dK, dV: accumulated by one CTA pair in TMEM
     if deterministic:
         assert torch.equal(g0[0], g1[0])

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 echo "== guard build: forward / backward / varlen / kvcache tests"
 FA_B200_LIB=flash_attention_b200/variants/lib_guard.so timeout 1500 python -m pytest tests/test_fwd_gpu.py tests/test_bwd_gpu.py tests/test_bwd_stress_gpu.py tests/test_varlen_matrix_gpu.py tests/test_sched_dynamic_gpu.py tests/test_kvcache_gpu.py tests/test_fa2_fullsize_gpu.py -x -q 2>&1 | tail -15 | tee gpurun_out/r2g_guard.log
-if grep -q "failed\|error\|Timeout\|timeout" gpurun_out/r2g_guard.log; then echo "GUARD RUN FAILED - stopping"; exit 0; fi
+if grep -q " failed\|error\|Timeout\|timeout" gpurun_out/r2g_guard.log; then echo "GUARD RUN FAILED - stopping"; exit 0; fi
 echo "== default build: full suite"
 timeout 1800 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 | tee gpurun_out/r2g_pytest.log
 echo "== ABAB timing dynamic vs static"
