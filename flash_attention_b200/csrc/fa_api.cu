@@ -422,7 +422,12 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   int sms = num_sms() - std::max(0, a.sm_margin);
   if (sms < 1) sms = 1;
   int64_t ctas = int64_t(sms) * ctas_per_sm;
-  static const bool sched_dynamic = [] { const char* e = getenv("FA_B200_SCHED_DYNAMIC"); return e ? atoi(e) != 0 : true; }();
+  // Dynamic draws pay for themselves when the items are long (>= 24 key blocks; causal 8k forward +6 %, C3 +6 %, same lease,
+  // profiles/r02_sched_dynamic_abab.log); with 1-8 block items (causal 1k) the draw latency shows and the static deal,
+  // which has many rounds to even out, is 10 % faster.  FA_B200_SCHED_DYNAMIC=0 / 2 forces static / dynamic.
+  int sched_mode = 1;   // (read per call: the tests switch it)
+  if (const char* e = getenv("FA_B200_SCHED_DYNAMIC")) sched_mode = atoi(e);
+  const bool sched_dynamic = sched_mode == 2 || (sched_mode == 1 && a.seqlen_k >= 3072);
   int* sched_counter = (sched_dynamic && pl.sched_bytes && a.workspace && a.workspace_bytes >= pl.sched_off + sizeof(int))
                            ? reinterpret_cast<int*>(static_cast<char*>(a.workspace) + pl.sched_off) : nullptr;
   if (a.cu_seqlens_q) {

@@ -238,7 +238,8 @@ static int run_bwd_typed(const fa_b200_bwd_args& a, const BwdPlan& pl, bool varl
       const int64_t total = int64_t(kp.num_pairs) * hz_total;
       if (total > INT32_MAX) return set_error("too many work items");
       kp.total_items = int(total);
-      static const bool sched_dynamic = [] { const char* e = getenv("FA_B200_SCHED_DYNAMIC"); return e ? atoi(e) != 0 : true; }();
+      bool sched_dynamic = true;   // (items of the pair kernel are long: always worth it; FA_B200_SCHED_DYNAMIC=0: static deal)
+      if (const char* e = getenv("FA_B200_SCHED_DYNAMIC")) sched_dynamic = atoi(e) != 0;
       {
         const int sms = std::max(2, num_sms() - std::max(0, a.sm_margin));
         if (sched_dynamic && total > sms / 2) kp.sched_counter = reinterpret_cast<int*>(ws + pl.off_sched);

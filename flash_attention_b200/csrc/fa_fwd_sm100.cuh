@@ -108,7 +108,7 @@ struct FwdCfg {
   static constexpr int kTileBytes = kPanels * kPanelBytes;  // Q tile == K block == V block
   static constexpr int kSmemQ = kTiles * kTileBytes;
   static constexpr int kSmemKV = kStages * kTileBytes;
-  static constexpr int kNumBars = 2 + 2 * kStages + 18;   // + q_empty[2], o_free[2], v_start, sched_full[2], sched_empty[2]
+  static constexpr int kNumBars = 2 + 2 * kStages + 20;   // + q_empty[2], o_free[2], v_start, sched_full[2], sched_empty[2], o_half[2]
   static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");  // hd256 (1 tile, 194 KB) runs one CTA per SM
 };
@@ -167,6 +167,10 @@ __device__ unsigned int g_fwd_item_sm[192];
 #endif
 #ifndef FA_FWD_POLY_DEG_FP8
 #define FA_FWD_POLY_DEG_FP8 3
+#endif
+#ifndef FA_FWD_ONEPASS
+#define FA_FWD_ONEPASS 1    // 1: unmasked blocks take the exponentials against the STALE reference maximum in one pass (no row-max
+                            // reduction in front of them); a row-sum guard catches the rows whose reference has to move
 #endif
 #ifndef FA_FWD_EXP_PIPE
 #define FA_FWD_EXP_PIPE 1   // 1: software-pipelined exponential phase (see the softmax loop); 0: the round-1 loop
@@ -400,6 +404,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   // still being computed -- a timing-dependent wrong result in split-KV decode with seqlen_k % 128 != 0.)
   const uint32_t bar_v_start = sBar + 8u * (15 + 2 * S);
   const uint32_t bar_sched_full0 = sBar + 8u * (16 + 2 * S), bar_sched_empty0 = sBar + 8u * (18 + 2 * S);
+  auto bar_o_half = [&](int i) { return sBar + 8u * (20 + 2 * S + i); };   // first half of the block's P V has landed in O_i
   const uint32_t sTmemPtr = sBar + 8u * Cfg::kNumBars;
   FwdSched sched;
   sched.G = G; sched.cta = cta; sched.total = total_items; sched.rounds = rounds; sched.k = 0;
@@ -426,6 +431,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         mbar_init(bar_p_full(i) + 16, 4);
         mbar_init(bar_o_full(i), 1);
         mbar_init(bar_o_free(i), 4);
+        mbar_init(bar_o_half(i), 1);
       }
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_kv_full(s), 1);
@@ -597,6 +603,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
               mbar_wait(bar_p_full(i), blk[i] & 1, 230 + i);
               tc_fence_after();
               issue_pv(i, sv, !first_pv[i], 0);
+              mma_commit(bar_o_half(i));   // (only waited for when the softmax has to move its reference mid-block)
               mbar_wait(bar_p_full(i) + 16, blk[i] & 1, 232 + i);
               tc_fence_after();
               issue_pv(i, sv, !first_pv[i], 1);
@@ -707,6 +714,10 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       float slope = 0.f;
       if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + head] / scale_eff;
 
+      constexpr bool kOnePass = FA_FWD_ONEPASS && FA_FWD_EXP_PIPE && !kFp8 && !kDropout;
+      constexpr float kGuard = 16384.f;   // one-pass blocks: largest half-row sum of exp2(x) taken without moving the reference
+                                          // (every term is then <= 2^14: finite in fp16 P, and far inside fp32 for the sums)
+      const float inv_scale_log2 = 1.0f / scale_log2;
       float m_ref = kNegInf, row_sum = 0.f;
       for (int it = it_lo; it < it_hi; ++it, ++blk) {
         const int j = w.n_max - 1 - it;
@@ -722,8 +733,21 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
         const bool slow = need_mask || has_softcap || p.alibi_slopes != nullptr ||
                           (p.debug_s != nullptr && it == 0 && r == 0);
-        float mx;
-        if (!slow) {
+        // One-pass blocks (unmasked, not the tile's first): no row maximum in front of the exponentials.  Softmax is
+        // invariant to the reference as long as nothing overflows, so P = exp2((s - m_ref) * scale) is formed against the
+        // reference left by the earlier blocks and a guard on the half-row sums (plain adds the loop has anyway) finds the
+        // rows whose scores outgrew it; only those warps stop, take the maximum and redo the half (fix_half below).  The
+        // row-max reduction -- 64 FMNMX3 and ~0.5k clk of the S -> P latency that paces the two-tile ping-pong -- is off the
+        // common path (profiles/r02_fwd_timeline_r1_vs_pipelined.log: "S ok -> max done").
+        const bool opt = kOnePass && !slow && it != it_lo;
+        float mx = 0.f;
+        if (opt) {
+          tmem_ld_x32(tS + 0, su);
+          tmem_ld_x32(tS + 32, su + 32);
+          tmem_wait_ld();
+          tmem_ld_x32(tS + 64, su + 64);   // waited for in front of the fifth chunk
+          tmem_ld_x32(tS + 96, su + 96);
+        } else if (!slow) {
           // fast path: second half of the row streams out of TMEM while the first half is reduced
           tmem_ld_x32(tS + 0, su);
           tmem_ld_x32(tS + 32, su + 32);
@@ -785,7 +809,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         // ---- online softmax: row max with a lazily updated reference (exact after normalisation)
         if (wq == 0 && lane == 0 && r == 0) FTS(9 + 4 * tile);
         const float m_new = fmaxf(m_ref, mx);
-        if (it == it_lo) {
+        if (opt) {
+          // reference untouched
+        } else if (it == it_lo) {
           m_ref = m_new;
         } else {
           bool need = (m_new - m_ref) * scale_log2 > kLagLog2;  // NaN (-inf - -inf) compares false
@@ -814,7 +840,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         // ---- P = exp2(S*scale_log2 - m*scale_log2), written back over S as packed 16-bit.
         // Packed FFMA2 for the scaling; a share of the pairs takes the FMA-pipe polynomial instead
         // of MUFU.EX2 (the MUFU unit, 16 op/clk/SM, is otherwise as busy as the tensor pipe).
-        const uint64_t sc2 = pack2(scale_log2, scale_log2), ng2 = pack2(neg_ms, neg_ms);
+        const uint64_t sc2 = pack2(scale_log2, scale_log2);
+        uint64_t ng2 = pack2(neg_ms, neg_ms);
         uint64_t acc_a = pack2(0.f, 0.f), acc_b = pack2(0.f, 0.f);
 #if FA_FWD_EXP_PIPE
         if constexpr (!kDropout) {
@@ -833,9 +860,62 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           for (int c = 0; c < 16; c += 2)
             unpack2(fma2(pack2(s[16 * k + c], s[16 * k + c + 1]), sc, ng2), s[16 * k + c], s[16 * k + c + 1]);
         };
+        // one-pass blocks: move the reference of the rows that need it to the maximum of half h (columns 64h .. 64h+63) and
+        // redo that half.  s[] holds x = (s - m_ref) * scale_log2 + kPOffset for columns [0, hi) (m_ref = -inf: x = s *
+        // scale_log2 + kPOffset), so the raw scores are never needed again.  Cold path: plain loops, MUFU only.
+        float hs0 = 0.f, xm_poly = -INFINITY;
+        auto fix_half = [&](const int h, const float hs) {
+          float mxx = s[64 * h];
+#pragma unroll
+          for (int c = 1; c < 64; ++c) mxx = fmaxf(mxx, s[64 * h + c]);
+          const bool had_ref = m_ref != kNegInf;
+          const bool need = !had_ref || !(hs <= kGuard) || xm_poly > 100.f;
+          // (with a reference in place it only ever moves up: the half's own maximum may lie below it)
+          const float delta = need ? (had_ref ? fmaxf(mxx - kPOffset, 0.f) : mxx - kPOffset) : 0.f;
+          const float f = (need && had_ref) ? ex2(-delta) : 1.0f;
+          // everything accumulated so far -- O (earlier blocks, and the first half of this one if h == 1) and the row sum --
+          // moves to the new reference
+          if (h == 0) mbar_wait(bar_o_full(tile), (blk - 1) & 1, 311 + tile);
+          else mbar_wait(bar_o_half(tile), blk & 1, 313 + tile);
+          tc_fence_after();
+          tmem_wait_st();
+#pragma unroll
+          for (int cc = 0; cc < kD; cc += 32) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + cc, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+            tmem_st_x32(tO + cc, o);
+          }
+          row_sum *= f;
+          if (need) m_ref = (had_ref ? m_ref : 0.f) + delta * inv_scale_log2;
+          const int hi = h == 0 ? 80 : 128;   // chunks already scaled (the software pipeline runs one chunk ahead)
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= 64 * h && c < hi) s[c] -= delta;
+          ng2 = add2(ng2, pack2(-delta, -delta));
+          float sum = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 32) {
+            uint32_t pk2[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float e0 = ex2(s[64 * h + cc + c]), e1 = ex2(s[64 * h + cc + c + 1]);
+              sum += e0 + e1;
+              pk2[c / 2] = Elt<T>::pack(e0, e1);
+            }
+            tmem_st_x16(tS + (64 * h + cc) / 2, pk2);
+          }
+          xm_poly = -INFINITY;
+          acc_a = pack2((h == 0 ? 0.f : hs0 * f) + sum, 0.f);
+          acc_b = pack2(0.f, 0.f);
+          return (h == 0 ? 0.f : hs0 * f) + sum;
+        };
         stage_a(0, sc2);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+          if (k == 3) tmem_wait_ld();   // one-pass blocks: columns 64..127 were still streaming out of TMEM
           if (k + 1 < 8) stage_a(k + 1, k == 0 ? sc2 : fma2(tok_prev, zero2, sc2));
           float ee[4];
 #pragma unroll
@@ -846,12 +926,22 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
               e0 = ex2(s[col]);
               e1 = ex2(s[col + 1]);
             } else {
+              // (the polynomial wraps around above 2^127 instead of returning inf: the guard watches its inputs)
+              if constexpr (kOnePass) xm_poly = fmax3(xm_poly, s[col], s[col + 1]);
               ex2_poly2_nz(pack2(s[col], s[col + 1]), e0, e1);
             }
             const uint64_t e2 = pack2(e0, e1);
             if (c & 2) acc_b = add2(acc_b, e2);
             else acc_a = add2(acc_a, e2);
-            if (c == 10) { tok_prev = tok_cur; tok_cur = e2; }
+            if (c == 10) {
+              tok_prev = tok_cur;
+              if constexpr (kOnePass) {   // an exponential against a stale reference may be inf: inf * 0 would poison the scale
+                const float tk = fminf(e0, 1.0f);
+                tok_cur = pack2(tk, tk);
+              } else {
+                tok_cur = e2;
+              }
+            }
             if constexpr (kFp8) {
               ee[c & 2] = e0;
               ee[(c & 2) + 1] = e1;
@@ -865,6 +955,18 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
             if constexpr (kFp8) tmem_st_x8(tS + cc / 4, pk);
             else tmem_st_x16(tS + cc / 2, pk);
             if (cc == 32 || cc == 96) {  // half of P is in TMEM: let the first / second half of P V start
+              if constexpr (kOnePass) {
+                if (opt) {   // guard: is every exponential of this half finite and small enough to keep the reference?
+                  float a0, a1, b0, b1;
+                  unpack2(acc_a, a0, a1);
+                  unpack2(acc_b, b0, b1);
+                  float hs = (a0 + a1) + (b0 + b1);
+                  if (cc == 96) hs -= hs0;            // this half's own sum (inf / NaN survive the subtraction)
+                  const bool bad = m_ref == kNegInf || !(hs <= kGuard) || xm_poly > 100.f;
+                  if (__any_sync(0xffffffffu, bad)) hs = fix_half(cc == 96 ? 1 : 0, hs);
+                  if (cc == 32) hs0 = hs;
+                }
+              }
               tmem_wait_st();
               tc_fence_before();
               __syncwarp();

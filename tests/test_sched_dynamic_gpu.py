@@ -11,6 +11,12 @@ from tests.util import bwd_tolerances, check_fwd, make_qkv
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _force_dynamic(monkeypatch):
+    # the forward only draws dynamically from 24 key blocks per item on (shorter items: static deal); 2 = always
+    monkeypatch.setenv("FA_B200_SCHED_DYNAMIC", "2")
+
+
 @pytest.fixture(scope="module")
 def ops():
     import flash_attention_b200 as m
@@ -42,6 +48,10 @@ def test_forward_few_ctas(ops, b, sq, sk, h, hk, d, causal, window, ctas):
     out1, lse1, _, _ = ops.fwd(q, k, v, sm_margin=_margin(ctas), **kw)
     assert torch.equal(out0, out1) and torch.equal(lse0, lse1)
     check_fwd(out1, lse1, q, k, v, causal=causal, window=window)
+    import os
+    os.environ["FA_B200_SCHED_DYNAMIC"] = "0"   # and the static deal of the same few-CTA grid
+    out2, lse2, _, _ = ops.fwd(q, k, v, sm_margin=_margin(ctas), **kw)
+    assert torch.equal(out0, out2) and torch.equal(lse0, lse2)
 
 
 def test_forward_varlen_few_ctas(ops):
