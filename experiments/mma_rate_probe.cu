@@ -15,7 +15,7 @@ template <int kCtas>
 __device__ __forceinline__ void body(long long* out, int mode, int n, int N) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
-  const uint32_t bar = base + 65536, tptr = base + 65536 + 16;
+  const uint32_t bar = base + 163840, tptr = base + 163840 + 16;   // (N = 256 operands reach beyond the first 64 KB)
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int idx = tid; idx < 65536 / 4; idx += blockDim.x) reinterpret_cast<uint32_t*>(smem)[idx] = 0;
@@ -29,7 +29,7 @@ __device__ __forceinline__ void body(long long* out, int mode, int n, int N) {
   tc_fence_before();
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 65536 + 16);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 163840 + 16);
   // mode: 0 SS K-major, 1 TS (A from TMEM cols 256..), 2 SS MN-major A+B, 3 (pair only) M=128 SS MN-major
   if (rank == 0 && warp == 1 && elect_one()) {
     const uint32_t M = kCtas == 2 ? (mode == 3 ? 128 : 256) : 128;
@@ -77,8 +77,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate2(long long
 int main() {
   long long* d;
   cudaMalloc(&d, 16);
-  cudaFuncSetAttribute(rate1, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
-  cudaFuncSetAttribute(rate2, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+  cudaFuncSetAttribute(rate1, cudaFuncAttributeMaxDynamicSharedMemorySize, 161 * 1024);
+  cudaFuncSetAttribute(rate2, cudaFuncAttributeMaxDynamicSharedMemorySize, 161 * 1024);
   const char* names[4] = {"SS K-major", "TS (A in TMEM), B MN-major", "SS MN-major A and B", "SS MN-major, M=128 pair (64 rows/CTA)"};
   for (int N : {64, 128, 256}) {
     const int n = 512;
@@ -87,8 +87,8 @@ int main() {
         if (mode == 2) continue;
         long long h[2] = {0, 0};
         for (int rep = 0; rep < 2; ++rep) {
-          if (ctas == 1) rate1<<<1, 128, 66 * 1024>>>(d, mode, n, N);
-          else rate2<<<2, 128, 66 * 1024>>>(d, mode, n, N);
+          if (ctas == 1) rate1<<<1, 128, 161 * 1024>>>(d, mode, n, N);
+          else rate2<<<2, 128, 161 * 1024>>>(d, mode, n, N);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         }

@@ -14,6 +14,7 @@
 #include "fa_api_common.h"
 #include "fa_combine.cuh"
 #include "fa_fwd_sm100.cuh"
+#include "fa_fwd_wide_sm100.cuh"
 #include "fa_kvcache.cuh"
 
 namespace fa {
@@ -153,7 +154,12 @@ int splits_heuristic(int ctas, int sms, int n_blocks, int max_splits) {
 
 enum FwdMode { kDense = 0, kVarlen = 1, kKvcache = 2 };
 
+#ifndef FA_B200_WIDE_DEFAULT
+#define FA_B200_WIDE_DEFAULT 0
+#endif
+
 struct FwdPlan {
+  int wide;      // 1: the wide-S kernel (one 128-row query tile per CTA, 256-key block pairs)
   int tiles;     // query tiles per CTA: 2 = throughput config (1 CTA/SM), 1 = latency config (2 CTAs/SM)
   int kD;        // padded head dim of the kernel (64 or 128)
   int gp;        // packed heads
@@ -232,6 +238,22 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     if (pl->kD == 256) pl->tiles = 1;  // S (128) + O (256) TMEM columns: one tile per CTA (forward only)
     if (pl->dropout) pl->tiles = 1;    // the dropout kernels are only instantiated for the 1-tile configuration
   }
+  // Wide-S kernel (fa_fwd_wide_sm100.cuh: S = Q K^T 256 keys at a time, one query tile per CTA): dense fp16 / bf16, head
+  // dim <= 128 in the 128 configuration, plain / causal / local masks only, long key streams.  FA_B200_FWD_WIDE=0/1 forces.
+  pl->wide = 0;
+  {
+    const bool eligible = mode == kDense && a.dtype != FA_B200_FP8_E4M3 && pl->kD == 128 && !pl->dropout && a.softcap == 0.f &&
+                          !a.alibi_slopes && !a.seqused_k && !a.seqused_q && !a.debug_s && a.num_splits <= 1 && a.pack_gqa != 1 &&
+                          a.seqlen_q > 128;
+    int wide_env = -1;   // (read per call: the tests switch it)
+    if (const char* e = getenv("FA_B200_FWD_WIDE")) wide_env = atoi(e);
+    int est_blocks = cdiv(a.seqlen_k, 128);
+    if (pl->has_left) est_blocks = std::min(est_blocks, cdiv(wl + std::max(wr, 0) + 256, 128));
+    if (eligible && (wide_env == 1 || (wide_env < 0 && FA_B200_WIDE_DEFAULT && est_blocks >= 16))) {
+      pl->wide = 1;
+      pl->tiles = 1;
+    }
+  }
   const int rows_cta = 128 * pl->tiles;
   // GQA head packing: fold the g query heads of one KV head into the M dimension when a CTA's worth of query
   // positions would otherwise be mostly empty (decode / short queries).
@@ -239,7 +261,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   if (a.pack_gqa == 1 && g > 1) {
     if (!is_pow2(g) || g > 128) return set_error("pack_gqa needs a power-of-two group size <= 128");
     gp = g;
-  } else if (a.pack_gqa == 0 && g > 1 && is_pow2(g) && g <= 128 && !pl->dropout) {
+  } else if (a.pack_gqa == 0 && g > 1 && is_pow2(g) && g <= 128 && !pl->dropout && !pl->wide) {
     const int sq = a.seqlen_q;
     const double eff_unpacked = double(sq) / (cdiv(sq, rows_cta) * rows_cta);
     const double eff_packed = double(sq) * g / (cdiv(sq * g, rows_cta) * rows_cta);
@@ -250,7 +272,7 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
   // split-KV (flash_api.cpp:317-347): heuristic when num_splits == 0; never for packed-varlen q
   int splits = a.num_splits;
   if (splits < 0) return set_error("num_splits must be non-negative");
-  if (pl->dropout) {
+  if (pl->dropout || pl->wide) {
     splits = 1;  // flash_api.cpp:331: the reference only splits when p_dropout == 0
   } else if (mode == kVarlen) {
     if (a.block_table && splits > 1) return set_error("num_splits > 1 is not supported for varlen paged KV");
@@ -318,6 +340,20 @@ static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t 
   return tiles == 1 ? launch_fwd_kernel_t<T, kD, 1>(kp, grid, stream) : launch_fwd_kernel_t<T, kD, 2>(kp, grid, stream);
 }
 
+template <typename T>
+static int launch_fwd_wide(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+  static PerDeviceOnce configured;
+  auto kern = fa_fwd_wide_kernel<T>;
+  if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdWideCfg::kSmemBytes); });
+      e != cudaSuccess)
+    return set_error(std::string("cudaFuncSetAttribute(fwd wide): ") + cudaGetErrorString(e));
+  kern<<<grid, FwdWideCfg::kThreads, FwdWideCfg::kSmemBytes, stream>>>(kp);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(std::string("fa_fwd_wide_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream) {
   FwdPlan pl;
   if (!a.q || !a.k || !a.v || !a.out || !a.softmax_lse) return set_error("q, k, v, out, softmax_lse must be non-null");
@@ -362,6 +398,10 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     if (nb == 1) str[2] = rows * str[0];
     uint32_t box[4] = {panel, 128, 1, 1};
     if (int rc = make_tmap(which == 0 ? &kp.tm_k : &kp.tm_v, dt, 4, base, dims, str, box)) return rc;
+    if (pl.wide) {
+      uint32_t box2[4] = {panel, 256, 1, 1};
+      if (int rc = make_tmap(which == 0 ? &kp.tm_k256 : &kp.tm_v256, dt, 4, base, dims, str, box2)) return rc;
+    }
   }
   kp.o = a.out;
   kp.lse = a.softmax_lse;
@@ -418,7 +458,7 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   const int64_t total_items = int64_t(pl.num_m_blocks) * hz_total;
   if (total_items > INT32_MAX) return set_error("too many work items");
   kp.total_items = int(total_items);
-  const int ctas_per_sm = pl.tiles == 1 && pl.kD != 256 ? 2 : 1;
+  const int ctas_per_sm = pl.tiles == 1 && pl.kD != 256 && !pl.wide ? 2 : 1;
   int sms = num_sms() - std::max(0, a.sm_margin);
   if (sms < 1) sms = 1;
   int64_t ctas = int64_t(sms) * ctas_per_sm;
@@ -449,7 +489,9 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
   }
   dim3 grid(unsigned(ctas), 1, 1);
   int rc;
-  if (fp8) {
+  if (pl.wide) {
+    rc = a.dtype == FA_B200_BF16 ? launch_fwd_wide<__nv_bfloat16>(kp, grid, stream) : launch_fwd_wide<__half>(kp, grid, stream);
+  } else if (fp8) {
     rc = launch_fwd_kernel<fp8_e4m3, 128>(kp, grid, stream, pl.tiles);
   } else if (a.dtype == FA_B200_BF16) {
     rc = pl.kD == 64 ? launch_fwd_kernel<__nv_bfloat16, 64>(kp, grid, stream, pl.tiles, pl.dropout)

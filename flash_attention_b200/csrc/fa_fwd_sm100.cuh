@@ -42,6 +42,8 @@ struct FwdKernelParams {
   CUtensorMap tm_q;  // 5-D: (d, gp, rows, h/gp, b)      box (64, gp, 128/gp, 1, 1)
   CUtensorMap tm_k;  // 4-D: (d, rows, h_k, b|pages|1)   box (64, 128, 1, 1)
   CUtensorMap tm_v;
+  CUtensorMap tm_k256;  // wide-S kernel (fa_fwd_wide_sm100.cuh): the same tensors with a box of 256 rows
+  CUtensorMap tm_v256;
   void* o;
   float* lse;
   float* o_accum;    // (splits, b, h, sq, kD) fp32 when num_splits > 1
@@ -172,6 +174,19 @@ __device__ unsigned int g_fwd_item_sm[192];
 #define FA_FWD_ONEPASS 1    // 1: unmasked blocks take the exponentials against the STALE reference maximum in one pass (no row-max
                             // reduction in front of them); a row-sum guard catches the rows whose reference has to move
 #endif
+#ifndef FA_FWD_SUM_LATE
+#define FA_FWD_SUM_LATE 0   // 1 (two-pass blocks only): the row sum is taken AFTER the block's P has been handed to the MMA thread
+                            // (the exponentials stay in the score registers), i.e. off the S -> P latency that paces the
+                            // two-tile ping-pong (the reference does the same: flash_attn/cute/flash_fwd_sm100.py:2545-2546)
+#endif
+#ifndef FA_FWD_ORGUARD
+#define FA_FWD_ORGUARD 0    // 1 (bf16 one-pass blocks): the guard of the stale-reference blocks is an OR over the packed 16-bit
+                            // P words (P is written as 2^(x - 13): bit 14 of a bf16 exponent field <=> x >= 14) instead of the
+                            // half-row sums, so the row sum can run late as well; fp16 kernels fall back to two-pass blocks
+#endif
+#ifndef FA_FWD_PSPLIT
+#define FA_FWD_PSPLIT 64    // columns of P handed to the MMA thread with the first arrive (64 or 96; the rest with the second)
+#endif
 #ifndef FA_FWD_EXP_PIPE
 #define FA_FWD_EXP_PIPE 1   // 1: software-pipelined exponential phase (see the softmax loop); 0: the round-1 loop
 #endif
@@ -184,6 +199,8 @@ __device__ unsigned int g_fwd_item_sm[192];
 #ifndef FA_FWD_POLY_PAIRS
 #define FA_FWD_POLY_PAIRS 1  // measured on B200 (r01): 0 -> 1315, 1 -> 1339, 2 -> 1307, 3 -> 1147, 4 -> 1046 TFLOP/s fwd
 #endif
+
+template <int kV> struct HalfIdx { static constexpr int value = kV; };
 
 // ---------------------------------------------------------------------------------------------- work items
 struct FwdWork {
@@ -376,6 +393,12 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
   constexpr float kNegInf = -INFINITY;
   constexpr int kPolyDeg = kFp8 ? FA_FWD_POLY_DEG_FP8 : 3;
   constexpr int kPolyPairs = kFp8 ? FA_FWD_POLY_PAIRS_FP8 : FA_FWD_POLY_PAIRS;
+  constexpr bool kBf16 = !kFp8 && Elt<T>::kFmt == 1;
+  constexpr bool kOrGuard = FA_FWD_ORGUARD && FA_FWD_ONEPASS && FA_FWD_EXP_PIPE && kBf16 && !kDropout;
+  constexpr bool kOnePassK = FA_FWD_ONEPASS && FA_FWD_EXP_PIPE && !kFp8 && !kDropout && (kOrGuard || !FA_FWD_ORGUARD);
+  constexpr int kPSplit = kOnePassK ? 64 : FA_FWD_PSPLIT;   // (the one-pass guard works on halves)
+  static_assert(kPSplit == 64 || kPSplit == 96, "FA_FWD_PSPLIT");
+  constexpr bool kSumLate = FA_FWD_SUM_LATE && FA_FWD_EXP_PIPE && !kDropout && !kFp8 && (!kOnePassK || kOrGuard);
 
   // ------------------------------------------------------------------ item enumeration (identical in every role)
   const int G = int(gridDim.x), cta = int(blockIdx.x);
@@ -544,9 +567,10 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         const uint32_t lb = lo_of(sKV + slot_v * Cfg::kTileBytes) | lo_mn;
         constexpr int kSteps = 4 * kBytes;              // MMAs per 128 keys (K = 16 keys for 16-bit, 32 for fp8)
         constexpr uint32_t kStepBytes = 4096 / kBytes;  // that many key rows of 128 B
+        constexpr int kFirst = kSteps * kPSplit / 128;  // MMAs covered by the first P arrive
 #pragma unroll
-        for (int k4 = 0; k4 < kSteps / 2; ++k4) {
-          const int kk = half * (kSteps / 2) + k4;
+        for (int kk = 0; kk < kSteps; ++kk) {
+          if ((kk < kFirst) != (half == 0)) continue;
           mma_ts<kFp8>(tO[i], tS[i] + kk * 8, mk(hi_mn, lb + kk * (kStepBytes >> 4)), idesc_pv, (acc || kk > 0) ? 1u : 0u);
         }
       };
@@ -557,8 +581,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       for (int L = sched.first(); L >= 0; L = sched.next(false, 0)) {
         FwdWork w;
         if (!fwd_decode_work<kRowsPerCta, kTiles>(p, L, w) || w.nblocks == 0) continue;
-        const int it = 0;  // (FTS below refers to the first item's iterations only)
-        (void)it;
+        const bool ts_item = q_items[0] + q_items[1] == 0;   // (the FTS stamps refer to the CTA's first item only)
+        (void)ts_item;
         bool act[2], first_pv[2];
 #pragma unroll
         for (int i = 0; i < kTiles; ++i) {
@@ -584,6 +608,8 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           const int sv = ring_v % S, sk_ = ring_k % S;
           const uint32_t phv = (ring_v / S) & 1, phk = (ring_k / S) & 1;
           const bool more = it2 + 1 < w.nblocks;
+          const int it = ts_item ? it2 : -1;
+          (void)it;
           if (it2 == 0 && w.v_tail) { mbar_wait(bar_v_clean, vclean_cnt & 1, 221); ++vclean_cnt; }  // rows beyond seqlen_k zeroed
           else mbar_wait(bar_kv_full(sv), phv, 220);
           bool k_waited = false;
@@ -601,13 +627,16 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
                 if (q_items[i] > 0) mbar_wait(bar_o_free(i), (q_items[i] - 1) & 1, 225 + i);
               }
               mbar_wait(bar_p_full(i), blk[i] & 1, 230 + i);
+              FTS(0 + 4 * i);
               tc_fence_after();
               issue_pv(i, sv, !first_pv[i], 0);
               mma_commit(bar_o_half(i));   // (only waited for when the softmax has to move its reference mid-block)
               mbar_wait(bar_p_full(i) + 16, blk[i] & 1, 232 + i);
+              FTS(1 + 4 * i);
               tc_fence_after();
               issue_pv(i, sv, !first_pv[i], 1);
               mma_commit(bar_o_full(i));
+              FTS(2 + 4 * i);
               first_pv[i] = false;
               ++blk[i];
               if (i == last_pv) mma_commit(bar_kv_empty(sv));
@@ -620,6 +649,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
               }
               issue_qk(i, sk_);
               mma_commit(bar_s_full(i));
+              FTS(3 + 4 * i);
               if (it2 + 2 == w.it_hi(i)) mma_commit(bar_q_empty(i));   // that was the item's last read of Q_i
               if (i == last_qk) mma_commit(bar_kv_empty(sk_));
             }
@@ -701,7 +731,9 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       // 2^-9 .. 448, so fp8 shifts P up by 2^5 and allows a lag of 2^3: P <= 2^8, and probabilities down to
       // 2^-14 of the row max survive the cast (the reference scales by 2^8 with no lag, flash_fwd_sm100.py:2190;
       // with a zero lag almost every block rescales: 32 rows per warp, each a new max with probability ~1/j).
-      constexpr float kPOffset = kFp8 ? 5.0f : 0.0f;
+      // (OR-guard kernels: P = 2^(x - 13), so that "x >= 14" is the top exponent bit of the bf16 word; the power of two
+      // cancels exactly in O / row_sum and bf16 has the exponent range to spare)
+      constexpr float kPOffset = kFp8 ? 5.0f : (kOrGuard ? -13.0f : 0.0f);
       constexpr float kLagLog2 = kFp8 ? 3.0f : 8.0f;
       // tile-level limits for the "does this block need masking" test
       const int t_row_lo = row0 + tile * 128;
@@ -714,7 +746,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
       float slope = 0.f;
       if (p.alibi_slopes) slope = p.alibi_slopes[bidb * p.alibi_batch_stride + head] / scale_eff;
 
-      constexpr bool kOnePass = FA_FWD_ONEPASS && FA_FWD_EXP_PIPE && !kFp8 && !kDropout;
+      constexpr bool kOnePass = kOnePassK;
       constexpr float kGuard = 16384.f;   // one-pass blocks: largest half-row sum of exp2(x) taken without moving the reference
                                           // (every term is then <= 2^14: finite in fp16 P, and far inside fp32 for the sums)
       const float inv_scale_log2 = 1.0f / scale_log2;
@@ -854,6 +886,7 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
         // multiplicand, which the assembler cannot fold): A(k+1) can only issue while B(k) is in flight, so both pipes stay busy.
         const uint64_t zero2 = pack2(0.f, 0.f);
         uint32_t pk[16];
+        uint32_t g_or = 0, g_or2 = 0;   // OR of the half's packed P words (two chains)
         uint64_t tok_prev = zero2, tok_cur = zero2;   // an exponential pair of chunk k-1 / k
         auto stage_a = [&](int k, uint64_t sc) {
 #pragma unroll
@@ -912,6 +945,80 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           acc_b = pack2(0.f, 0.f);
           return (h == 0 ? 0.f : hs0 * f) + sum;
         };
+        // OR-guard variant of the same cold path.  The exponentials have replaced the scaled scores in s[] (late row sum), so
+        // the half's scores come out of TMEM again: P occupies TMEM columns 0..63, so columns 64..127 of S are never
+        // overwritten, and at the guard of the first half only the P words of columns 0..31 have been stored (TMEM columns
+        // 0..15) -- the scaled scores of columns 0..15 are still in s[] (chunk 0 is summed early for that reason).
+        // Fills lo[] / hi[] with the redone P words of columns 64h..64h+31 / 64h+32..64h+63.
+        auto fix_half_or = [&](auto hc, uint32_t* lo, uint32_t* hi) {
+          constexpr int h = decltype(hc)::value;   // (a run-time half index would turn s[] into a local-memory array)
+          float nm0, nm1;
+          unpack2(ng2, nm0, nm1);
+          if (h == 0) {
+            tmem_ld_x16(tS + 16, su + 16);
+            tmem_ld_x32(tS + 32, su + 32);
+          } else {
+            tmem_ld_x32(tS + 64, su + 64);
+            tmem_ld_x32(tS + 96, su + 96);
+          }
+          tmem_wait_ld();
+          float* x = s + 64 * h;   // scaled scores of the half against the OLD reference
+#pragma unroll
+          for (int c = (h == 0 ? 16 : 0); c < 64; ++c) x[c] = fmaf(x[c], scale_log2, nm0);
+          float xmax = x[0];
+#pragma unroll
+          for (int c = 1; c < 64; ++c) xmax = fmaxf(xmax, x[c]);
+          const bool had_ref = m_ref != kNegInf;
+          const float xm = xmax - kPOffset;            // the half's maximum above the reference, log2 units
+          const bool need = !had_ref || xm > kLagLog2;
+          const float delta = need ? xm : 0.f;
+          const float f = (need && had_ref) ? ex2(-delta) : 1.0f;
+          // everything accumulated so far -- O (earlier blocks, and the first half of this one if h == 1) and the sums --
+          // moves to the new reference
+          if (h == 0) mbar_wait(bar_o_full(tile), (blk - 1) & 1, 311 + tile);
+          else mbar_wait(bar_o_half(tile), blk & 1, 313 + tile);
+          tc_fence_after();
+          tmem_wait_st();
+#pragma unroll
+          for (int cc = 0; cc < kD; cc += 32) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + cc, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+            tmem_st_x32(tO + cc, o);
+          }
+          row_sum *= f;
+          if (need) m_ref = (had_ref ? m_ref : 0.f) + delta * inv_scale_log2;
+          ng2 = add2(ng2, pack2(-delta, -delta));
+          float sum0 = 0.f;
+          if (h == 0) {
+#pragma unroll
+            for (int c = 64; c < 80; ++c) s[c] -= delta;   // the software pipeline has scaled one chunk ahead
+          } else {
+#pragma unroll
+            for (int c = 16; c < 64; ++c) s[c] *= f;         // the first half's exponentials wait for the late row sum
+            float a0, a1, b0, b1;                            // (chunk 0 has been summed already)
+            unpack2(acc_a, a0, a1);
+            unpack2(acc_b, b0, b1);
+            sum0 = ((a0 + a1) + (b0 + b1)) * f;
+          }
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) {
+            const float e0 = ex2(x[c] - delta), e1 = ex2(x[c + 1] - delta);
+            if (h == 0 && c < 16) {
+              sum0 += e0 + e1;
+            } else {
+              x[c] = e0;
+              x[c + 1] = e1;
+            }
+            if (c < 32) lo[c / 2] = Elt<T>::pack(e0, e1);
+            else hi[(c - 32) / 2] = Elt<T>::pack(e0, e1);
+          }
+          acc_a = pack2(sum0, 0.f);
+          acc_b = pack2(0.f, 0.f);
+          xm_poly = -INFINITY;
+        };
         stage_a(0, sc2);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -931,8 +1038,13 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
               ex2_poly2_nz(pack2(s[col], s[col + 1]), e0, e1);
             }
             const uint64_t e2 = pack2(e0, e1);
-            if (c & 2) acc_b = add2(acc_b, e2);
-            else acc_a = add2(acc_a, e2);
+            if (kSumLate && !(kOrGuard && col < 16)) {   // (OR-guard kernels: chunk 0 is summed here and keeps its scaled
+              s[col] = e0;                               //  scores -- its S columns are the ones the first P store overwrites)
+              s[col + 1] = e1;
+            } else {
+              if (c & 2) acc_b = add2(acc_b, e2);
+              else acc_a = add2(acc_a, e2);
+            }
             if (c == 10) {
               tok_prev = tok_cur;
               if constexpr (kOnePass) {   // an exponential against a stale reference may be inf: inf * 0 would poison the scale
@@ -947,15 +1059,43 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
               ee[(c & 2) + 1] = e1;
               if (c & 2) pk[(col & 31) / 4] = pack_e4m3x4(ee[0], ee[1], ee[2], ee[3]);
             } else {
-              pk[(col & 31) / 2] = Elt<T>::pack(e0, e1);
+              const uint32_t w = Elt<T>::pack(e0, e1);
+              pk[(col & 31) / 2] = w;
+              if constexpr (kOrGuard) {
+                if (c & 2) g_or2 |= w;
+                else g_or |= w;
+              }
             }
           }
           if (k & 1) {   // 32 columns done
             const int cc = 32 * (k >> 1);
-            if constexpr (kFp8) tmem_st_x8(tS + cc / 4, pk);
+            if constexpr (kOrGuard) {
+              if (cc == 32 || cc == 96) {
+                if (opt) {   // guard: no exponential of this half reached 2^14 (inf included), and the polynomial saw no huge input
+#ifdef FA_FWD_OG_NOFIX   // TIMING EXPERIMENT ONLY: the guard never fires
+                  const bool bad = false;
+#else
+                  const bool bad = m_ref == kNegInf || ((g_or | g_or2) & 0x40004000u) != 0u || xm_poly > 100.f;
+#endif
+                  if (__any_sync(0xffffffffu, bad)) {
+                    uint32_t lo[16];
+                    if (cc == 32) {
+                      fix_half_or(HalfIdx<0>{}, lo, pk);
+                      tmem_st_x16(tS + 0, lo);
+                    } else {
+                      fix_half_or(HalfIdx<1>{}, lo, pk);
+                      tmem_st_x16(tS + 32, lo);
+                    }
+                  }
+                }
+                g_or = 0;
+                g_or2 = 0;
+              }
+              tmem_st_x16(tS + cc / 2, pk);
+            } else if constexpr (kFp8) tmem_st_x8(tS + cc / 4, pk);
             else tmem_st_x16(tS + cc / 2, pk);
-            if (cc == 32 || cc == 96) {  // half of P is in TMEM: let the first / second half of P V start
-              if constexpr (kOnePass) {
+            if (cc + 32 == kPSplit || cc == 96) {  // first part / all of P is in TMEM: let the first / second part of P V start
+              if constexpr (kOnePass && !kOrGuard) {
                 if (opt) {   // guard: is every exponential of this half finite and small enough to keep the reference?
                   float a0, a1, b0, b1;
                   unpack2(acc_a, a0, a1);
@@ -971,9 +1111,21 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_p_full(tile) + (cc == 96 ? 16u : 0u));
-              if (wq == 0 && lane == 0) FTS((cc == 96 ? 11 : 10) + 4 * tile);
+              if (wq == 0 && lane == 0 && r == 0) FTS((cc == 96 ? 11 : 10) + 4 * tile);
             }
           }
+        }
+        if constexpr (kSumLate) {   // P is on its way: the row sum runs while the MMA thread works for this tile
+          uint64_t acc_c = pack2(0.f, 0.f), acc_d = pack2(0.f, 0.f);
+#pragma unroll
+          for (int c = kOrGuard ? 16 : 0; c < 128; c += 8) {
+            acc_a = add2(acc_a, pack2(s[c], s[c + 1]));
+            acc_b = add2(acc_b, pack2(s[c + 2], s[c + 3]));
+            acc_c = add2(acc_c, pack2(s[c + 4], s[c + 5]));
+            acc_d = add2(acc_d, pack2(s[c + 6], s[c + 7]));
+          }
+          acc_a = add2(acc_a, acc_c);
+          acc_b = add2(acc_b, acc_d);
         }
         } else
 #endif
@@ -1013,12 +1165,12 @@ fa_fwd_kernel(const __grid_constant__ FwdKernelParams p) {
           }
           if constexpr (kFp8) tmem_st_x8(tS + cc / 4, pk);
           else tmem_st_x16(tS + cc / 2, pk);
-          if (cc == 32 || cc == 96) {  // half of P is in TMEM: let the first / second half of P V start
+          if (cc + 32 == kPSplit || cc == 96) {  // first part / all of P is in TMEM: let the first / second part of P V start
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_p_full(tile) + (cc == 96 ? 16u : 0u));
-            if (wq == 0 && lane == 0) FTS((cc == 96 ? 11 : 10) + 4 * tile);
+            if (wq == 0 && lane == 0 && r == 0) FTS((cc == 96 ? 11 : 10) + 4 * tile);
           }
         }
         }

@@ -1,0 +1,459 @@
+// fa_fwd_wide_sm100.cuh — forward attention, head dim 128, S computed 256 keys at a time ("wide S").
+//
+// Why: the measured cost of a tcgen05.mma on B200 is `10 + N/2` clk (+31 when A comes from shared memory)
+// per K = 16 step (experiments/mma_rate_probe.cu, profiles/r02_mma_rate_probe_n256.txt): the fixed part is paid per
+// INSTRUCTION.  The two-tile kernel (fa_fwd_sm100.cuh) issues S = Q K^T with N = 128 (105 clk, 61 % of peak) and sits
+// within 10 % of the resulting issue floor of 2864 clk per (256 queries x 128 keys) -- as does the reference's Blackwell
+// kernel (flash_attn/cute/flash_fwd_sm100.py, same shape).  With N = 256 the same S costs 169 clk per 256 keys (76 %),
+// i.e. 2536 clk for the same work (-11.5 %).  256 S columns per query tile leave TMEM room for ONE query tile per CTA
+// (S 256 + P 128 + O 128 = 512 columns), so the overlap of softmax and tensor pipe comes from a different place than
+// the two-tile ping-pong:
+//
+//   * P does NOT alias S here: S is free again as soon as the softmax warps have read it into registers, so the MMA
+//     thread issues  QK(g+1)  BEFORE  PV(g)  and the tensor pipe works on the next block pair while the softmax of the
+//     current one runs (a software pipeline of depth two over the stream of 256-key block pairs, ACROSS work items).
+//   * the 256 columns of a block pair are split between two softmax warpgroups (same 128 query rows: thread t of
+//     either group owns row t).  They agree on the row maximum through a 1 KB shared-memory exchange + one named
+//     barrier per block pair, keep partial row sums (joined in the epilogue) and each rescales / writes out half of
+//     the O columns.
+//
+//   warp 0-3   softmax group A: S columns [0,128) of the pair   -> P columns [0,128)   O columns [0,64)
+//   warp 4-7   softmax group B: S columns [128,256)             -> P columns [128,256) O columns [64,128)
+//   warp 8     MMA issuer (one elected thread)
+//   warp 9     TMA producer: Q tile, K / V block pairs (256 rows x 128, 64 KB) through a 3-slot ring,
+//              in consumption order  K(g), V(g-1), K(g+1), V(g), ...
+//
+// Scope (the host picks this kernel only then, plan_fwd): dense (batch, seq, head, dim) tensors, fp16 / bf16, head
+// dim <= 128, causal / local / no mask, no dropout / softcap / ALiBi / split-KV / paged KV / packed GQA.  Semantics
+// as in fa_fwd_sm100.cuh (reference: csrc/flash_attn/src/flash_fwd_kernel.h, mask.h:172-173, softmax.h:169-186).
+#pragma once
+#include "fa_fwd_sm100.cuh"
+
+namespace fa {
+
+struct FwdWideCfg {
+  static constexpr int kThreads = 384;
+  static constexpr int kRegsSoftmax = 216, kRegsOther = 72;   // 2 * 216 + 72 = 504 = 3 * 168
+  static constexpr int kSlots = 3;
+  static constexpr int kSlotBytes = 65536;        // a K or V block pair: 2 panels x (256 rows x 128 B)
+  static constexpr int kPanelBytesKV = 32768;
+  static constexpr int kPanelBytesQ = 16384;
+  static constexpr int kSQ = 0;
+  static constexpr int kSKV = 32768;
+  static constexpr int kSBar = kSKV + kSlots * kSlotBytes;
+  static constexpr int kNumBars = 20;
+  static constexpr int kSMisc = kSBar + 8 * kNumBars;     // tmem pointer (4 B), pad, 2 scheduler items
+  static constexpr int kSExch = kSMisc + 32;              // float [2 parities][2 groups][128 rows]
+  static constexpr int kSmemBytes = kSExch + 2048;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <typename T>
+__global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(const __grid_constant__ FwdKernelParams p) {
+  using Cfg = FwdWideCfg;
+  constexpr int kD = 128;
+  constexpr float kNegInf = -INFINITY;
+  constexpr float kLagLog2 = 8.0f;
+
+  const int G = int(gridDim.x), cta = int(blockIdx.x);
+  const int total_items = p.total_items;
+  const int rounds = (total_items + G - 1) / G;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  const uint32_t sQ = smem_base + Cfg::kSQ, sKV = smem_base + Cfg::kSKV, sBar = smem_base + Cfg::kSBar;
+  enum { Q_FULL = 0, Q_EMPTY = 1, KV_FULL0 = 2, KV_EMPTY0 = 5, S_FULL = 8, S_READ = 9, P_FULL0 = 10, PV_DONE0 = 12,
+         O_FREE = 14, SCHED_FULL0 = 15, SCHED_EMPTY0 = 17 };
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  const uint32_t sTmemPtr = smem_base + Cfg::kSMisc;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::kSMisc);
+  float* exch = reinterpret_cast<float*>(smem_raw + Cfg::kSExch);
+
+  FwdSched sched;
+  sched.G = G; sched.cta = cta; sched.total = total_items; sched.rounds = rounds; sched.k = 0;
+  sched.bar_full0 = bar(SCHED_FULL0); sched.bar_empty0 = bar(SCHED_EMPTY0); sched.item_addr = sTmemPtr + 8u;
+  sched.dyn = p.sched_counter != nullptr;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q);
+    tma_prefetch_desc(&p.tm_k256);
+    tma_prefetch_desc(&p.tm_v256);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(bar(Q_FULL), 1);
+      mbar_init(bar(Q_EMPTY), 1);
+      for (int s = 0; s < Cfg::kSlots; ++s) {
+        mbar_init(bar(KV_FULL0 + s), 1);
+        mbar_init(bar(KV_EMPTY0 + s), 1);
+      }
+      mbar_init(bar(S_FULL), 1);
+      mbar_init(bar(S_READ), 8);     // every softmax warp has S in registers
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(bar(P_FULL0 + h), 4);
+        mbar_init(bar(PV_DONE0 + h), 1);
+        mbar_init(bar(SCHED_FULL0 + h), 1);
+        mbar_init(bar(SCHED_EMPTY0 + h), 9);   // MMA thread + 8 softmax warps
+      }
+      mbar_init(bar(O_FREE), 8);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(sTmemPtr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // block-pair range of a work item: 128-key blocks [n_min, n_max) -> pairs [p_lo, p_hi), streamed right to left
+  auto pair_range = [](const FwdWork& w, int& p_lo, int& p_hi) {
+    p_lo = w.n_min >> 1;
+    p_hi = (w.n_max + 1) >> 1;
+    if (w.nblocks == 0) p_lo = p_hi = 0;
+  };
+
+  if (warp >= 8) {
+    reg_dealloc<Cfg::kRegsOther>();
+    // ================================================================== TMA producer
+    if (warp == 9) {
+      if (elect_one()) {
+        int ring = 0, q_cnt = 0;
+        bool pend = false;
+        int pv_row = 0, pv_hk = 0, pv_b = 0;
+        int nxt = -1;
+        bool drawn = false;
+        auto load_pair = [&](const CUtensorMap* tm, int row, int hk, int b) {
+          const int s = ring % Cfg::kSlots;
+          const uint32_t ph = (ring / Cfg::kSlots) & 1;
+          mbar_wait(bar(KV_EMPTY0 + s), ph ^ 1, 100 + s);
+          mbar_arrive_expect_tx(bar(KV_FULL0 + s), Cfg::kSlotBytes);
+#pragma unroll
+          for (int pn = 0; pn < 2; ++pn)
+            tma_load_4d(sKV + s * Cfg::kSlotBytes + pn * Cfg::kPanelBytesKV, tm, bar(KV_FULL0 + s), pn * 64, row, hk, b);
+          ++ring;
+        };
+        auto advance = [&]() -> int {
+          if (!sched.dyn) return sched.next(false, 0);
+          if (!drawn) nxt = sched.draw(p.sched_counter);
+          drawn = false;
+          return sched.publish(nxt);
+        };
+        for (int L = sched.first(); L >= 0; L = advance()) {
+          FwdWork w;
+          if (!fwd_decode_work<128, 1>(p, L, w)) continue;
+          int p_lo, p_hi;
+          pair_range(w, p_lo, p_hi);
+          const int N = p_hi - p_lo;
+          if (N == 0) continue;
+          if (q_cnt > 0) mbar_wait(bar(Q_EMPTY), (q_cnt - 1) & 1, 110);
+          ++q_cnt;
+          mbar_arrive_expect_tx(bar(Q_FULL), 32768);
+#pragma unroll
+          for (int pn = 0; pn < 2; ++pn)
+            tma_load_5d(sQ + pn * Cfg::kPanelBytesQ, &p.tm_q, bar(Q_FULL), pn * 64, 0, w.row0, w.slot, w.bidb);
+          for (int n = 0; n < N; ++n) {
+            if (sched.dyn && !drawn && n + 2 >= N) {
+              nxt = sched.draw(p.sched_counter);
+              drawn = true;
+            }
+            const int row = (p_hi - 1 - n) * 256;
+            load_pair(&p.tm_k256, row, w.hk_idx, w.bidb);
+            if (pend) load_pair(&p.tm_v256, pv_row, pv_hk, pv_b);
+            pend = true; pv_row = row; pv_hk = w.hk_idx; pv_b = w.bidb;
+          }
+        }
+        if (pend) load_pair(&p.tm_v256, pv_row, pv_hk, pv_b);
+      }
+      __syncwarp();
+    }
+    // ================================================================== MMA issuer
+    else if (warp == 8) {
+      if (elect_one()) {
+        constexpr uint32_t fmt = Elt<T>::kFmt;
+        constexpr uint32_t idesc_qk = make_idesc(fmt, fmt, 0, 0, 128, 256);
+        constexpr uint32_t idesc_pv = make_idesc(fmt, fmt, 0, 1, 128, kD);
+        constexpr uint64_t desc_k_major = smem_desc_sw128(16, 1024);
+        constexpr uint64_t desc_mn_major = smem_desc_sw128(Cfg::kPanelBytesKV, 1024);
+        constexpr uint32_t hi_k = uint32_t(desc_k_major >> 32), hi_mn = uint32_t(desc_mn_major >> 32);
+        constexpr uint32_t lo_mn = uint32_t(desc_mn_major);
+        auto lo_of = [](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
+        auto mk = [](uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; };
+        const uint32_t tS = tmem_base, tP = tmem_base + 256, tO = tmem_base + 384;
+
+        int ring = 0, g = 0, items = 0;
+        bool pend = false;
+        bool pd_first = false;
+        int pd_g = 0, pd_item = 0;
+        auto do_pv = [&]() {
+          const int rv = ring++;
+          const int sv = rv % Cfg::kSlots;
+          mbar_wait(bar(KV_FULL0 + sv), (rv / Cfg::kSlots) & 1, 220);
+          if (pd_first && pd_item > 0) mbar_wait(bar(O_FREE), (pd_item - 1) & 1, 225);   // the previous item's O has been read out
+          const uint32_t lb = lo_of(sKV + sv * Cfg::kSlotBytes) | lo_mn;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar(P_FULL0 + h), pd_g & 1, 230 + h);
+            tc_fence_after();
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const int kk = 8 * h + k8;   // 16 keys per step
+              mma_ts<false>(tO, tP + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), idesc_pv, (!pd_first || kk > 0) ? 1u : 0u);
+            }
+            mma_commit(bar(PV_DONE0 + h));
+          }
+          mma_commit(bar(KV_EMPTY0 + sv));
+        };
+        for (int L = sched.first(); L >= 0; L = sched.next(false, 0)) {
+          FwdWork w;
+          if (!fwd_decode_work<128, 1>(p, L, w)) continue;
+          int p_lo, p_hi;
+          pair_range(w, p_lo, p_hi);
+          const int N = p_hi - p_lo;
+          if (N == 0) continue;
+          mbar_wait(bar(Q_FULL), items & 1, 200);
+          for (int n = 0; n < N; ++n) {
+            const int rk = ring++;
+            const int sk_ = rk % Cfg::kSlots;
+            mbar_wait(bar(KV_FULL0 + sk_), (rk / Cfg::kSlots) & 1, 210);
+            if (g > 0) mbar_wait(bar(S_READ), (g - 1) & 1, 211);   // S of the previous block pair is in registers
+            tc_fence_after();
+            {
+              const uint32_t la = lo_of(sQ) | uint32_t(desc_k_major);
+              const uint32_t lb = lo_of(sKV + sk_ * Cfg::kSlotBytes) | uint32_t(desc_k_major);
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {   // 16 head-dim elements (32 B) per step
+                const uint32_t offa = ((kk / 4) * Cfg::kPanelBytesQ + (kk % 4) * 32) >> 4;
+                const uint32_t offb = ((kk / 4) * Cfg::kPanelBytesKV + (kk % 4) * 32) >> 4;
+                mma_ss<false>(tS, mk(hi_k, la + offa), mk(hi_k, lb + offb), idesc_qk, kk > 0);
+              }
+            }
+            mma_commit(bar(S_FULL));
+            mma_commit(bar(KV_EMPTY0 + sk_));
+            if (n == N - 1) mma_commit(bar(Q_EMPTY));
+            if (pend) do_pv();
+            pend = true; pd_first = n == 0; pd_g = g; pd_item = items;
+            ++g;
+          }
+          ++items;
+        }
+        if (pend) do_pv();
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================== softmax warpgroups
+    reg_alloc<Cfg::kRegsSoftmax>();
+    const int h = warp >> 2;          // key half of the block pair
+    const int wq = warp & 3;
+    const int trow = wq * 32 + lane;  // row of the query tile == TMEM lane
+    const uint32_t lane_sel = uint32_t(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + 128 * h;
+    const uint32_t tP = tmem_base + lane_sel + 256 + 64 * h;
+    const uint32_t tO = tmem_base + lane_sel + 384 + 64 * h;
+    int g = 0, items = 0;
+    for (int L = sched.first(); L >= 0; L = sched.next(true, lane)) {
+      FwdWork w;
+      if (!fwd_decode_work<128, 1>(p, L, w)) continue;
+      int p_lo, p_hi;
+      pair_range(w, p_lo, p_hi);
+      const int N = p_hi - p_lo;
+      const int bidb = w.bidb, head = w.slot, shift = w.shift, sk_b = w.sk_b;
+      const int qpos = w.row0 + trow;
+      const bool row_valid = qpos < w.rows_total;
+      const float scale_log2 = p.scale_log2;
+      const int t_qlo = w.row0;
+      const int t_qhi = w.row0 + 127 < w.rows_total - 1 ? w.row0 + 127 : w.rows_total - 1;
+      int col_hi = sk_b, col_lo = 0;
+      if (p.has_right) { int l = qpos + 1 + shift + p.wr; col_hi = l < col_hi ? l : col_hi; }
+      if (p.has_left) { int l = qpos + shift - p.wl; col_lo = l > 0 ? l : 0; }
+
+      float m_ref = kNegInf, row_sum = 0.f;
+      for (int n = 0; n < N; ++n, ++g) {
+        const int col0 = (p_hi - 1 - n) * 256 + 128 * h;
+        mbar_wait(bar(S_FULL), g & 1, 300 + h);
+        tc_fence_after();
+        uint32_t su[128];
+        float* s = reinterpret_cast<float*>(su);
+        tmem_ld_x32(tS + 0, su);
+        tmem_ld_x32(tS + 32, su + 32);
+        tmem_ld_x32(tS + 64, su + 64);
+        tmem_ld_x32(tS + 96, su + 96);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(S_READ));   // the MMA thread may overwrite S with the next block pair
+        bool need_mask = col0 + 128 > sk_b;
+        if (p.has_right) need_mask |= col0 + 128 > t_qlo + 1 + shift + p.wr;
+        if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
+        if (need_mask) {
+          const int hi = col_hi - col0, lo = col_lo - col0;
+#pragma unroll
+          for (int c = 0; c < 128; ++c) s[c] = (c >= hi || c < lo) ? kNegInf : s[c];
+        }
+        float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]);
+        float m2 = fmax3(s[6], s[7], s[8]), m3 = fmax3(s[9], s[10], s[11]);
+#pragma unroll
+        for (int c = 12; c + 7 < 128; c += 8) {
+          m0 = fmax3(m0, s[c], s[c + 1]);
+          m1 = fmax3(m1, s[c + 2], s[c + 3]);
+          m2 = fmax3(m2, s[c + 4], s[c + 5]);
+          m3 = fmax3(m3, s[c + 6], s[c + 7]);
+        }
+        m0 = fmax3(m0, s[124], s[125]);
+        m1 = fmax3(m1, s[126], s[127]);
+        float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // ---- the two groups agree on the row maximum of the whole block pair
+        float* ex = exch + (g & 1) * 256;
+        ex[h * 128 + trow] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(mx, ex[(1 - h) * 128 + trow]);
+        // ---- online softmax with a lazily updated reference (both groups take identical decisions: same inputs)
+        const float m_new = fmaxf(m_ref, mx);
+        if (n == 0) {
+          m_ref = m_new;
+        } else {
+          bool need = (m_new - m_ref) * scale_log2 > kLagLog2;   // NaN (-inf - -inf) compares false
+          if (m_ref == kNegInf) {
+            m_ref = m_new;
+            need = false;
+          }
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(bar(PV_DONE0 + 1), (g - 1) & 1, 310 + h);   // P V of the previous block pair has landed
+            tc_fence_after();
+            const float f = need ? ex2((m_ref - m_new) * scale_log2) : 1.0f;
+#pragma unroll
+            for (int cc = 0; cc < 64; cc += 32) {   // this group's half of the O columns
+              uint32_t o[32];
+              tmem_ld_x32(tO + cc, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+              tmem_st_x32(tO + cc, o);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            // both halves of the O row must be rescaled before EITHER group hands its P to the MMA thread (the first P V step
+            // accumulates into all 128 columns): the two warps that own these 32 rows meet on their own named barrier
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory");
+            row_sum *= f;
+            if (need) m_ref = m_new;
+          }
+        }
+        const float neg_ms = (m_ref == kNegInf) ? 0.f : -m_ref * scale_log2;
+        // ---- P = exp2(S * scale_log2 - m * scale_log2): software-pipelined as in fa_fwd_sm100.cuh (scaling of chunk k+1
+        // made to depend on an exponential of chunk k-1, so that MUFU and FMA pipes run side by side); all 64 packed
+        // words stay in registers (they replace the scores they came from) until the P buffer is free.
+        const uint64_t sc2 = pack2(scale_log2, scale_log2);
+        const uint64_t ng2 = pack2(neg_ms, neg_ms);
+        const uint64_t zero2 = pack2(0.f, 0.f);
+        uint64_t acc_a = zero2, acc_b = zero2;
+        uint32_t pk[64];
+        uint64_t tok_prev = zero2, tok_cur = zero2;
+        auto stage_a = [&](int k, uint64_t sc) {
+#pragma unroll
+          for (int c = 0; c < 16; c += 2)
+            unpack2(fma2(pack2(s[16 * k + c], s[16 * k + c + 1]), sc, ng2), s[16 * k + c], s[16 * k + c + 1]);
+        };
+        stage_a(0, sc2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k + 1 < 8) stage_a(k + 1, k == 0 ? sc2 : fma2(tok_prev, zero2, sc2));
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const int col = 16 * k + c;
+            float e0, e1;
+            if ((c >> 1) < 8 - FA_FWD_POLY8) {
+              e0 = ex2(s[col]);
+              e1 = ex2(s[col + 1]);
+            } else {
+              ex2_poly2_nz(pack2(s[col], s[col + 1]), e0, e1);
+            }
+            const uint64_t e2 = pack2(e0, e1);
+            if (c & 2) acc_b = add2(acc_b, e2);
+            else acc_a = add2(acc_a, e2);
+            if (c == 10) {
+              tok_prev = tok_cur;
+              tok_cur = e2;
+            }
+            pk[col / 2] = Elt<T>::pack(e0, e1);
+          }
+        }
+        if (g > 0) mbar_wait(bar(PV_DONE0 + h), (g - 1) & 1, 320 + h);   // the previous block pair's P V has read this half of P
+        tc_fence_after();
+        tmem_st_x16(tP + 0, pk);
+        tmem_st_x16(tP + 16, pk + 16);
+        tmem_st_x16(tP + 32, pk + 32);
+        tmem_st_x16(tP + 48, pk + 48);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(P_FULL0 + h));
+        {
+          float a0, a1, b0, b1;
+          unpack2(acc_a, a0, a1);
+          unpack2(acc_b, b0, b1);
+          row_sum += (a0 + a1) + (b0 + b1);
+        }
+      }
+
+      // ---------------------------------------------------------------- epilogue: join the row sums, write half of O
+      {
+        float* ex = exch + (g & 1) * 256;
+        ex[h * 128 + trow] = row_sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        row_sum += ex[(1 - h) * 128 + trow];
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // (the next item's first exchange reuses this buffer)
+      }
+      float inv = 0.f, lse_val;
+      const bool dead = m_ref == kNegInf || !(row_sum > 0.f);
+      if (!dead) {
+        inv = 1.0f / row_sum;
+        lse_val = m_ref * p.scale + __logf(row_sum);
+      } else {
+        lse_val = INFINITY;   // fully masked row (softmax.h:180)
+      }
+      uint32_t o[64] = {};
+      if (N > 0) {
+        mbar_wait(bar(PV_DONE0 + 1), (g - 1) & 1, 330 + h);
+        tc_fence_after();
+        tmem_ld_x32(tO + 0, o);
+        tmem_ld_x32(tO + 32, o + 32);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(O_FREE));
+        ++items;
+      }
+      if (row_valid) {
+        T* dst = reinterpret_cast<T*>(p.o) + bidb * p.o_batch_stride + int64_t(qpos) * p.o_row_stride +
+                 int64_t(head) * p.o_head_stride + 64 * h;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          if (64 * h + c < p.d) {   // d is a multiple of 8
+            uint4 v4;
+            v4.x = Elt<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+            v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+            v4.z = Elt<T>::pack(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+            v4.w = Elt<T>::pack(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c) = v4;
+          }
+        }
+        if (h == 0) p.lse[(int64_t(bidb) * p.h + head) * p.sq + qpos] = lse_val;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fa
