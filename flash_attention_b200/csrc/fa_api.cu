@@ -342,12 +342,13 @@ static int launch_fwd_kernel(const FwdKernelParams& kp, dim3 grid, cudaStream_t 
 
 template <typename T>
 static int launch_fwd_wide(const FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+  using Cfg = FwdWideCfg<FA_WIDE_GROUPS>;
   static PerDeviceOnce configured;
-  auto kern = fa_fwd_wide_kernel<T>;
-  if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdWideCfg::kSmemBytes); });
+  auto kern = fa_fwd_wide_kernel<T, FA_WIDE_GROUPS>;
+  if (cudaError_t e = configured.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
       e != cudaSuccess)
     return set_error(std::string("cudaFuncSetAttribute(fwd wide): ") + cudaGetErrorString(e));
-  kern<<<grid, FwdWideCfg::kThreads, FwdWideCfg::kSmemBytes, stream>>>(kp);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("fa_fwd_wide_kernel launch: ") + cudaGetErrorString(e));

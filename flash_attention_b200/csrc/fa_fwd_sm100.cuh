@@ -171,11 +171,15 @@ __device__ unsigned int g_fwd_item_sm[192];
 #define FA_FWD_POLY_DEG_FP8 3
 #endif
 #ifndef FA_FWD_ONEPASS
-#define FA_FWD_ONEPASS 1    // 1: unmasked blocks take the exponentials against the STALE reference maximum in one pass (no row-max
-                            // reduction in front of them); a row-sum guard catches the rows whose reference has to move
+#define FA_FWD_ONEPASS 0    // 1: unmasked blocks take the exponentials against the STALE reference maximum in one pass (no row-max
+                            // reduction in front of them); a row-sum guard catches the rows whose reference has to move.
+                            // Measured (profiles/r02_j_fwd_latesum_abab.log, same lease): two-pass 1258, one-pass 1279, two-pass
+                            // with the LATE row sum 1320 TFLOP/s at the C2 shape -- the late sum is the default, the one-pass
+                            // variants (their guards put work back on the S -> P chain, the OR guard costs registers:
+                            // profiles/r02_m_fwd_orguard_abab.log) stay as switches
 #endif
 #ifndef FA_FWD_SUM_LATE
-#define FA_FWD_SUM_LATE 0   // 1 (two-pass blocks only): the row sum is taken AFTER the block's P has been handed to the MMA thread
+#define FA_FWD_SUM_LATE 1   // 1 (two-pass blocks only): the row sum is taken AFTER the block's P has been handed to the MMA thread
                             // (the exponentials stay in the score registers), i.e. off the S -> P latency that paces the
                             // two-tile ping-pong (the reference does the same: flash_attn/cute/flash_fwd_sm100.py:2545-2546)
 #endif

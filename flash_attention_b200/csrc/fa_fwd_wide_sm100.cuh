@@ -12,16 +12,20 @@
 //   * P does NOT alias S here: S is free again as soon as the softmax warps have read it into registers, so the MMA
 //     thread issues  QK(g+1)  BEFORE  PV(g)  and the tensor pipe works on the next block pair while the softmax of the
 //     current one runs (a software pipeline of depth two over the stream of 256-key block pairs, ACROSS work items).
-//   * the 256 columns of a block pair are split between two softmax warpgroups (same 128 query rows: thread t of
-//     either group owns row t).  They agree on the row maximum through a 1 KB shared-memory exchange + one named
-//     barrier per block pair, keep partial row sums (joined in the epilogue) and each rescales / writes out half of
-//     the O columns.
+//   * the 256 columns of a block pair are split between kNG softmax warpgroups (same 128 query rows: thread t of
+//     every group owns row t).  The kNG warps that own the same 32 rows agree on the row maximum through a small
+//     shared-memory exchange + one named barrier of their own per block pair, keep partial row sums (joined in the
+//     epilogue) and each rescales / writes out 1/kNG of the O columns.  kNG = 4 (64 columns per thread, 16 softmax
+//     warps): with two groups the softmax of a block pair took 3.0k clk against the 2.5k of the tensor pipe
+//     (profiles/r02_q_wide_timeline_2groups.log: load + max 0.4k, exchange 0.25k, exponentials 2.0k, hand-over
+//     0.25k, both warps of a scheduler in the same phase at the same time); four warps per scheduler hide the latency
+//     phases behind each other's arithmetic.
 //
-//   warp 0-3   softmax group A: S columns [0,128) of the pair   -> P columns [0,128)   O columns [0,64)
-//   warp 4-7   softmax group B: S columns [128,256)             -> P columns [128,256) O columns [64,128)
-//   warp 8     MMA issuer (one elected thread)
-//   warp 9     TMA producer: Q tile, K / V block pairs (256 rows x 128, 64 KB) through a 3-slot ring,
-//              in consumption order  K(g), V(g-1), K(g+1), V(g), ...
+//   warp 0 .. 4 kNG - 1    softmax group h = warp / 4: S columns [kC h, kC h + kC) of the pair, kC = 256 / kNG
+//                          -> P columns of the same keys, O columns [128 h / kNG, 128 (h + 1) / kNG)
+//   warp 4 kNG             MMA issuer (one elected thread)
+//   warp 4 kNG + 1         TMA producer: Q tile, K / V block pairs (256 rows x 128, 64 KB) through a 3-slot ring,
+//                          in consumption order  K(g), V(g-1), K(g+1), V(g), ...
 //
 // Scope (the host picks this kernel only then, plan_fwd): dense (batch, seq, head, dim) tensors, fp16 / bf16, head
 // dim <= 128, causal / local / no mask, no dropout / softcap / ALiBi / split-KV / paged KV / packed GQA.  Semantics
@@ -29,11 +33,37 @@
 #pragma once
 #include "fa_fwd_sm100.cuh"
 
+#ifndef FA_WIDE_POLY8
+#define FA_WIDE_POLY8 2   // polynomial pairs out of every 8 pairs (16 scores)
+#endif
+#ifndef FA_WIDE_GROUPS
+#define FA_WIDE_GROUPS 2   // measured: 2 groups 1256, 4 groups 1212 TFLOP/s at the C2 shape (profiles/r02_r_wide_4groups_timing.log)
+#endif
+#ifndef FA_WIDE_DIAG
+#define FA_WIDE_DIAG 0   // TIMING EXPERIMENTS ONLY (wrong results): 1 = exponentials for half of the columns, 3 = every CTA streams the K / V of (batch 0, head 0) (L2-resident)
+#endif
+
+// timeline stamps of CTA 0's first work item (FA_FWD_TS builds; tools/probe_fwd_wide_ts.py)
+#define WTS(cond_, blk_, ev_)                     \
+  do {                                            \
+    if (cond_) {                                  \
+      const int it = (blk_);                      \
+      (void)it;                                   \
+      FTS(ev_);                                   \
+    }                                             \
+  } while (0)
+
 namespace fa {
 
+template <int kNG>
 struct FwdWideCfg {
-  static constexpr int kThreads = 384;
-  static constexpr int kRegsSoftmax = 216, kRegsOther = 72;   // 2 * 216 + 72 = 504 = 3 * 168
+  static_assert(kNG == 2 || kNG == 4, "softmax groups");
+  static constexpr int kC = 256 / kNG;            // S columns per softmax thread
+  static constexpr int kOC = 128 / kNG;           // O columns per softmax thread
+  static constexpr int kW = 4 * kNG;              // softmax warps
+  static constexpr int kThreads = 128 * (kNG + 1);
+  // register pool = kThreads x (65536 / kThreads rounded down to 8): 384 x 168 or 640 x 96
+  static constexpr int kRegsSoftmax = kNG == 2 ? 216 : 104, kRegsOther = kNG == 2 ? 72 : 64;
   static constexpr int kSlots = 3;
   static constexpr int kSlotBytes = 65536;        // a K or V block pair: 2 panels x (256 rows x 128 B)
   static constexpr int kPanelBytesKV = 32768;
@@ -43,15 +73,16 @@ struct FwdWideCfg {
   static constexpr int kSBar = kSKV + kSlots * kSlotBytes;
   static constexpr int kNumBars = 20;
   static constexpr int kSMisc = kSBar + 8 * kNumBars;     // tmem pointer (4 B), pad, 2 scheduler items
-  static constexpr int kSExch = kSMisc + 32;              // float [2 parities][2 groups][128 rows]
+  static constexpr int kSExch = kSMisc + 32;              // row maxima: uint16 [2 parities][kNG][128]; row sums: float [kNG][128]
   static constexpr int kSmemBytes = kSExch + 2048;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <typename T>
-__global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(const __grid_constant__ FwdKernelParams p) {
-  using Cfg = FwdWideCfg;
+template <typename T, int kNG>
+__global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kernel(const __grid_constant__ FwdKernelParams p) {
+  using Cfg = FwdWideCfg<kNG>;
   constexpr int kD = 128;
+  constexpr int kC = Cfg::kC, kOC = Cfg::kOC, kW = Cfg::kW;
   constexpr float kNegInf = -INFINITY;
   constexpr float kLagLog2 = 8.0f;
 
@@ -63,12 +94,13 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();
   const uint32_t sQ = smem_base + Cfg::kSQ, sKV = smem_base + Cfg::kSKV, sBar = smem_base + Cfg::kSBar;
-  enum { Q_FULL = 0, Q_EMPTY = 1, KV_FULL0 = 2, KV_EMPTY0 = 5, S_FULL = 8, S_READ = 9, P_FULL0 = 10, PV_DONE0 = 12,
-         O_FREE = 14, SCHED_FULL0 = 15, SCHED_EMPTY0 = 17 };
+  enum { Q_FULL = 0, Q_EMPTY = 1, KV_FULL0 = 2, KV_EMPTY0 = 5, S_FULL = 8, S_READ = 9, P_FULL = 10, PV_DONE = 11,
+         O_FREE = 12, SCHED_FULL0 = 13, SCHED_EMPTY0 = 15 };
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t sTmemPtr = smem_base + Cfg::kSMisc;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::kSMisc);
-  float* exch = reinterpret_cast<float*>(smem_raw + Cfg::kSExch);
+  uint16_t* exch_max = reinterpret_cast<uint16_t*>(smem_raw + Cfg::kSExch);
+  float* exch_sum = reinterpret_cast<float*>(smem_raw + Cfg::kSExch);
 
   FwdSched sched;
   sched.G = G; sched.cta = cta; sched.total = total_items; sched.rounds = rounds; sched.k = 0;
@@ -76,12 +108,13 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
   sched.dyn = p.sched_counter != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 9 && lane == 0) {
+  constexpr int kWarpMma = kW, kWarpTma = kW + 1;
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&p.tm_q);
     tma_prefetch_desc(&p.tm_k256);
     tma_prefetch_desc(&p.tm_v256);
   }
-  if (warp == 8) {
+  if (warp == kWarpMma) {
     if (lane == 0) {
       mbar_init(bar(Q_FULL), 1);
       mbar_init(bar(Q_EMPTY), 1);
@@ -90,14 +123,14 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
         mbar_init(bar(KV_EMPTY0 + s), 1);
       }
       mbar_init(bar(S_FULL), 1);
-      mbar_init(bar(S_READ), 8);     // every softmax warp has S in registers
-      for (int h = 0; h < 2; ++h) {
-        mbar_init(bar(P_FULL0 + h), 4);
-        mbar_init(bar(PV_DONE0 + h), 1);
-        mbar_init(bar(SCHED_FULL0 + h), 1);
-        mbar_init(bar(SCHED_EMPTY0 + h), 9);   // MMA thread + 8 softmax warps
+      mbar_init(bar(S_READ), kW);     // every softmax warp has its S columns in registers
+      mbar_init(bar(P_FULL), kW);
+      mbar_init(bar(PV_DONE), 1);
+      mbar_init(bar(O_FREE), kW);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar(SCHED_FULL0 + i), 1);
+        mbar_init(bar(SCHED_EMPTY0 + i), 1 + kW);   // MMA thread + softmax warps
       }
-      mbar_init(bar(O_FREE), 8);
       fence_barrier_init();
     }
     __syncwarp();
@@ -116,10 +149,10 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
     if (w.nblocks == 0) p_lo = p_hi = 0;
   };
 
-  if (warp >= 8) {
+  if (warp >= kW) {
     reg_dealloc<Cfg::kRegsOther>();
     // ================================================================== TMA producer
-    if (warp == 9) {
+    if (warp == kWarpTma) {
       if (elect_one()) {
         int ring = 0, q_cnt = 0;
         bool pend = false;
@@ -161,6 +194,9 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
               drawn = true;
             }
             const int row = (p_hi - 1 - n) * 256;
+#if FA_WIDE_DIAG == 3
+            w.hk_idx = 0; w.bidb = 0;
+#endif
             load_pair(&p.tm_k256, row, w.hk_idx, w.bidb);
             if (pend) load_pair(&p.tm_v256, pv_row, pv_hk, pv_b);
             pend = true; pv_row = row; pv_hk = w.hk_idx; pv_b = w.bidb;
@@ -171,7 +207,7 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
       __syncwarp();
     }
     // ================================================================== MMA issuer
-    else if (warp == 8) {
+    else if (warp == kWarpMma) {
       if (elect_one()) {
         constexpr uint32_t fmt = Elt<T>::kFmt;
         constexpr uint32_t idesc_qk = make_idesc(fmt, fmt, 0, 0, 128, 256);
@@ -187,25 +223,22 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
         int ring = 0, g = 0, items = 0;
         bool pend = false;
         bool pd_first = false;
-        int pd_g = 0, pd_item = 0;
+        int pd_g = 0, pd_item = 0, pd_n = 0;
         auto do_pv = [&]() {
           const int rv = ring++;
           const int sv = rv % Cfg::kSlots;
           mbar_wait(bar(KV_FULL0 + sv), (rv / Cfg::kSlots) & 1, 220);
           if (pd_first && pd_item > 0) mbar_wait(bar(O_FREE), (pd_item - 1) & 1, 225);   // the previous item's O has been read out
           const uint32_t lb = lo_of(sKV + sv * Cfg::kSlotBytes) | lo_mn;
+          mbar_wait(bar(P_FULL), pd_g & 1, 230);
+          WTS(pd_item == 0, pd_n, 1);
+          tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(bar(P_FULL0 + h), pd_g & 1, 230 + h);
-            tc_fence_after();
-#pragma unroll
-            for (int k8 = 0; k8 < 8; ++k8) {
-              const int kk = 8 * h + k8;   // 16 keys per step
-              mma_ts<false>(tO, tP + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), idesc_pv, (!pd_first || kk > 0) ? 1u : 0u);
-            }
-            mma_commit(bar(PV_DONE0 + h));
-          }
+          for (int kk = 0; kk < 16; ++kk)   // 16 keys per step
+            mma_ts<false>(tO, tP + kk * 8, mk(hi_mn, lb + kk * (2048 >> 4)), idesc_pv, (!pd_first || kk > 0) ? 1u : 0u);
+          mma_commit(bar(PV_DONE));
           mma_commit(bar(KV_EMPTY0 + sv));
+          WTS(pd_item == 0, pd_n, 2);
         };
         for (int L = sched.first(); L >= 0; L = sched.next(false, 0)) {
           FwdWork w;
@@ -233,9 +266,10 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
             }
             mma_commit(bar(S_FULL));
             mma_commit(bar(KV_EMPTY0 + sk_));
+            WTS(items == 0, n, 0);
             if (n == N - 1) mma_commit(bar(Q_EMPTY));
             if (pend) do_pv();
-            pend = true; pd_first = n == 0; pd_g = g; pd_item = items;
+            pend = true; pd_first = n == 0; pd_g = g; pd_item = items; pd_n = n;
             ++g;
           }
           ++items;
@@ -247,14 +281,16 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
   } else {
     // ================================================================== softmax warpgroups
     reg_alloc<Cfg::kRegsSoftmax>();
-    const int h = warp >> 2;          // key half of the block pair
+    const int h = warp >> 2;          // which kC columns of the block pair
     const int wq = warp & 3;
     const int trow = wq * 32 + lane;  // row of the query tile == TMEM lane
     const uint32_t lane_sel = uint32_t(wq * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + 128 * h;
-    const uint32_t tP = tmem_base + lane_sel + 256 + 64 * h;
-    const uint32_t tO = tmem_base + lane_sel + 384 + 64 * h;
-    int g = 0, items = 0;
+    const uint32_t tS = tmem_base + lane_sel + kC * h;
+    const uint32_t tP = tmem_base + lane_sel + 256 + (kC / 2) * h;
+    const uint32_t tO = tmem_base + lane_sel + 384 + kOC * h;
+    const uint32_t pbar = 2 + wq;     // named barrier of the kNG warps that own these 32 rows
+    auto partner_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(pbar), "n"(32 * kNG) : "memory"); };
+    int g = 0;
     for (int L = sched.first(); L >= 0; L = sched.next(true, lane)) {
       FwdWork w;
       if (!fwd_decode_work<128, 1>(p, L, w)) continue;
@@ -273,45 +309,81 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
 
       float m_ref = kNegInf, row_sum = 0.f;
       for (int n = 0; n < N; ++n, ++g) {
-        const int col0 = (p_hi - 1 - n) * 256 + 128 * h;
+        const int col0 = (p_hi - 1 - n) * 256 + kC * h;
         mbar_wait(bar(S_FULL), g & 1, 300 + h);
+        const bool ts_on = wq == 0 && lane == 0 && g == n && h < 2;   // (g == n: the CTA's first item)
+        WTS(ts_on, n, 4 + 6 * h);
         tc_fence_after();
-        uint32_t su[128];
+        uint32_t su[kC];
         float* s = reinterpret_cast<float*>(su);
-        tmem_ld_x32(tS + 0, su);
-        tmem_ld_x32(tS + 32, su + 32);
-        tmem_ld_x32(tS + 64, su + 64);
-        tmem_ld_x32(tS + 96, su + 96);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(S_READ));   // the MMA thread may overwrite S with the next block pair
-        bool need_mask = col0 + 128 > sk_b;
-        if (p.has_right) need_mask |= col0 + 128 > t_qlo + 1 + shift + p.wr;
+        bool need_mask = col0 + kC > sk_b;
+        if (p.has_right) need_mask |= col0 + kC > t_qlo + 1 + shift + p.wr;
         if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
-        if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < kC / 2; c += 32) tmem_ld_x32(tS + c, su + c);
+        tmem_wait_ld();
+        WTS(ts_on, n, 5 + 6 * h);
+#pragma unroll
+        for (int c = kC / 2; c < kC; c += 32) tmem_ld_x32(tS + c, su + c);   // streams out of TMEM while the first half is reduced
+        float mx;
+        if (!need_mask) {
+          float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]);
+          float m2 = fmax3(s[6], s[7], s[8]), m3 = fmax3(s[9], s[10], s[11]);
+#pragma unroll
+          for (int c = 12; c + 7 < kC / 2; c += 8) {
+            m0 = fmax3(m0, s[c], s[c + 1]);
+            m1 = fmax3(m1, s[c + 2], s[c + 3]);
+            m2 = fmax3(m2, s[c + 4], s[c + 5]);
+            m3 = fmax3(m3, s[c + 6], s[c + 7]);
+          }
+          m0 = fmax3(m0, s[kC / 2 - 4], s[kC / 2 - 3]);
+          m1 = fmax3(m1, s[kC / 2 - 2], s[kC / 2 - 1]);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(S_READ));   // the MMA thread may overwrite S with the next block pair
+#pragma unroll
+          for (int c = kC / 2; c + 7 < kC; c += 8) {
+            m0 = fmax3(m0, s[c], s[c + 1]);
+            m1 = fmax3(m1, s[c + 2], s[c + 3]);
+            m2 = fmax3(m2, s[c + 4], s[c + 5]);
+            m3 = fmax3(m3, s[c + 6], s[c + 7]);
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(S_READ));
           const int hi = col_hi - col0, lo = col_lo - col0;
 #pragma unroll
-          for (int c = 0; c < 128; ++c) s[c] = (c >= hi || c < lo) ? kNegInf : s[c];
-        }
-        float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]);
-        float m2 = fmax3(s[6], s[7], s[8]), m3 = fmax3(s[9], s[10], s[11]);
+          for (int c = 0; c < kC; ++c) s[c] = (c >= hi || c < lo) ? kNegInf : s[c];
+          float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]);
 #pragma unroll
-        for (int c = 12; c + 7 < 128; c += 8) {
-          m0 = fmax3(m0, s[c], s[c + 1]);
-          m1 = fmax3(m1, s[c + 2], s[c + 3]);
-          m2 = fmax3(m2, s[c + 4], s[c + 5]);
-          m3 = fmax3(m3, s[c + 6], s[c + 7]);
+          for (int c = 6; c + 3 < kC; c += 4) {
+            m0 = fmax3(m0, s[c], s[c + 1]);
+            m1 = fmax3(m1, s[c + 2], s[c + 3]);
+          }
+          mx = fmax3(m0, m1, fmaxf(s[kC - 2], s[kC - 1]));
         }
-        m0 = fmax3(m0, s[124], s[125]);
-        m1 = fmax3(m1, s[126], s[127]);
-        float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        // ---- the two groups agree on the row maximum of the whole block pair
-        float* ex = exch + (g & 1) * 256;
-        ex[h * 128 + trow] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mx = fmaxf(mx, ex[(1 - h) * 128 + trow]);
-        // ---- online softmax with a lazily updated reference (both groups take identical decisions: same inputs)
+        // ---- the kNG warps that own these 32 rows agree on the row maximum of the whole block pair.  The maxima travel as
+        // bf16 rounded UP (a reference slightly above the true maximum is as good as the maximum itself, and every partner
+        // sees the same kNG numbers, its own included), two parities deep: one named barrier per block pair is enough.
+        WTS(ts_on, n, 6 + 6 * h);
+        {
+          uint16_t* ex = exch_max + (g & 1) * (kNG * 128);
+          const uint32_t bits = __float_as_uint(mx);
+          ex[h * 128 + trow] = uint16_t((mx >= 0.f ? bits + 0xFFFFu : bits) >> 16);
+          partner_sync();
+          uint32_t mb = 0xFF80u;   // -inf
+          float mr = kNegInf;
+#pragma unroll
+          for (int i = 0; i < kNG; ++i) mr = fmaxf(mr, __uint_as_float(uint32_t(ex[i * 128 + trow]) << 16));
+          (void)mb;
+          mx = mr;
+        }
+        WTS(ts_on, n, 7 + 6 * h);
+        // ---- online softmax with a lazily updated reference (all groups take identical decisions: same inputs)
         const float m_new = fmaxf(m_ref, mx);
         if (n == 0) {
           m_ref = m_new;
@@ -322,11 +394,11 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
             need = false;
           }
           if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(bar(PV_DONE0 + 1), (g - 1) & 1, 310 + h);   // P V of the previous block pair has landed
+            mbar_wait(bar(PV_DONE), (g - 1) & 1, 310 + h);   // P V of the previous block pair has landed
             tc_fence_after();
             const float f = need ? ex2((m_ref - m_new) * scale_log2) : 1.0f;
 #pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {   // this group's half of the O columns
+            for (int cc = 0; cc < kOC; cc += 32) {   // this group's share of the O columns
               uint32_t o[32];
               tmem_ld_x32(tO + cc, o);
               tmem_wait_ld();
@@ -336,22 +408,22 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
             }
             tmem_wait_st();
             tc_fence_before();
-            // both halves of the O row must be rescaled before EITHER group hands its P to the MMA thread (the first P V step
-            // accumulates into all 128 columns): the two warps that own these 32 rows meet on their own named barrier
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory");
+            // every share of the O rows must be rescaled before ANY group hands its P to the MMA thread (the first P V step
+            // accumulates into all 128 columns)
+            partner_sync();
             row_sum *= f;
             if (need) m_ref = m_new;
           }
         }
         const float neg_ms = (m_ref == kNegInf) ? 0.f : -m_ref * scale_log2;
         // ---- P = exp2(S * scale_log2 - m * scale_log2): software-pipelined as in fa_fwd_sm100.cuh (scaling of chunk k+1
-        // made to depend on an exponential of chunk k-1, so that MUFU and FMA pipes run side by side); all 64 packed
-        // words stay in registers (they replace the scores they came from) until the P buffer is free.
+        // made to depend on an exponential of chunk k-1, so that MUFU and FMA pipes run side by side); the packed words
+        // stay in registers (they replace the scores they came from) until the P buffer is free.
         const uint64_t sc2 = pack2(scale_log2, scale_log2);
         const uint64_t ng2 = pack2(neg_ms, neg_ms);
         const uint64_t zero2 = pack2(0.f, 0.f);
         uint64_t acc_a = zero2, acc_b = zero2;
-        uint32_t pk[64];
+        uint32_t pk[kC / 2];
         uint64_t tok_prev = zero2, tok_cur = zero2;
         auto stage_a = [&](int k, uint64_t sc) {
 #pragma unroll
@@ -360,13 +432,20 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
         };
         stage_a(0, sc2);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (k + 1 < 8) stage_a(k + 1, k == 0 ? sc2 : fma2(tok_prev, zero2, sc2));
+        for (int k = 0; k < kC / 16; ++k) {
+#if FA_WIDE_DIAG == 1
+          if (k & 1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) pk[8 * k + c] = 0;
+            continue;
+          }
+#endif
+          if (k + 1 < kC / 16) stage_a(k + 1, k == 0 ? sc2 : fma2(tok_prev, zero2, sc2));
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
             const int col = 16 * k + c;
             float e0, e1;
-            if ((c >> 1) < 8 - FA_FWD_POLY8) {
+            if ((c >> 1) < 8 - FA_WIDE_POLY8) {
               e0 = ex2(s[col]);
               e1 = ex2(s[col + 1]);
             } else {
@@ -382,16 +461,16 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
             pk[col / 2] = Elt<T>::pack(e0, e1);
           }
         }
-        if (g > 0) mbar_wait(bar(PV_DONE0 + h), (g - 1) & 1, 320 + h);   // the previous block pair's P V has read this half of P
+        WTS(ts_on, n, 8 + 6 * h);
+        if (g > 0) mbar_wait(bar(PV_DONE), (g - 1) & 1, 320 + h);   // the previous block pair's P V has read P
         tc_fence_after();
-        tmem_st_x16(tP + 0, pk);
-        tmem_st_x16(tP + 16, pk + 16);
-        tmem_st_x16(tP + 32, pk + 32);
-        tmem_st_x16(tP + 48, pk + 48);
+#pragma unroll
+        for (int c = 0; c < kC / 2; c += 16) tmem_st_x16(tP + c, pk + c);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(P_FULL0 + h));
+        if (lane == 0) mbar_arrive(bar(P_FULL));
+        WTS(ts_on, n, 9 + 6 * h);
         {
           float a0, a1, b0, b1;
           unpack2(acc_a, a0, a1);
@@ -400,14 +479,14 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
         }
       }
 
-      // ---------------------------------------------------------------- epilogue: join the row sums, write half of O
-      {
-        float* ex = exch + (g & 1) * 256;
-        ex[h * 128 + trow] = row_sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        row_sum += ex[(1 - h) * 128 + trow];
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // (the next item's first exchange reuses this buffer)
-      }
+      // ---------------------------------------------------------------- epilogue: join the row sums, write this group's O columns
+      partner_sync();   // (the sums reuse the buffer of the maxima: every partner has read the last block pair's)
+      exch_sum[h * 128 + trow] = row_sum;
+      partner_sync();
+      row_sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < kNG; ++i) row_sum += exch_sum[i * 128 + trow];
+      partner_sync();   // (the next item's first exchange reuses the buffer)
       float inv = 0.f, lse_val;
       const bool dead = m_ref == kNegInf || !(row_sum > 0.f);
       if (!dead) {
@@ -416,24 +495,23 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
       } else {
         lse_val = INFINITY;   // fully masked row (softmax.h:180)
       }
-      uint32_t o[64] = {};
+      uint32_t o[kOC] = {};
       if (N > 0) {
-        mbar_wait(bar(PV_DONE0 + 1), (g - 1) & 1, 330 + h);
+        mbar_wait(bar(PV_DONE), (g - 1) & 1, 330 + h);
         tc_fence_after();
-        tmem_ld_x32(tO + 0, o);
-        tmem_ld_x32(tO + 32, o + 32);
+#pragma unroll
+        for (int c = 0; c < kOC; c += 32) tmem_ld_x32(tO + c, o + c);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(O_FREE));
-        ++items;
       }
       if (row_valid) {
         T* dst = reinterpret_cast<T*>(p.o) + bidb * p.o_batch_stride + int64_t(qpos) * p.o_row_stride +
-                 int64_t(head) * p.o_head_stride + 64 * h;
+                 int64_t(head) * p.o_head_stride + kOC * h;
 #pragma unroll
-        for (int c = 0; c < 64; c += 8) {
-          if (64 * h + c < p.d) {   // d is a multiple of 8
+        for (int c = 0; c < kOC; c += 8) {
+          if (kOC * h + c < p.d) {   // d is a multiple of 8
             uint4 v4;
             v4.x = Elt<T>::pack(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
             v4.y = Elt<T>::pack(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
@@ -450,7 +528,7 @@ __global__ void __launch_bounds__(FwdWideCfg::kThreads, 1) fa_fwd_wide_kernel(co
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
