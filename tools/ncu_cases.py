@@ -50,6 +50,9 @@ elif case == "hd64_causal":
     f = fwd_bwd(4, 8192, 32, 32, 64, True)
 elif case == "headline":
     f = fwd_bwd(4, 8192, 16, 16, 128, False)
+elif case == "headline_fwd":   # forward only (FA_B200_FWD_WIDE=1 selects the wide-S kernel)
+    q, k, v = (rnd(4, 8192, 16, 128) for _ in range(3))
+    f = lambda: fa.flash_attn_func(q, k, v)
 elif case == "headline_causal":
     f = fwd_bwd(4, 8192, 16, 16, 128, True)
 elif case == "c3":

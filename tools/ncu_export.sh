@@ -4,7 +4,7 @@
 # (the .ncu-rep itself stays in /tmp: five of them blew gpurun's 64 MiB return limit in round 2, call A).
 c=$1; reps=$2; skip=$3; cnt=$4; tag=$5
 rep=/tmp/ncu_$tag
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fa_fwd_kernel|fa_bwd|fa_combine' -s $skip -c $cnt -f -o $rep \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"${NCU_K:-fa_fwd_kernel|fa_fwd_wide|fa_bwd|fa_combine}" -s $skip -c $cnt -f -o $rep \
   python tools/ncu_cases.py $c $reps > gpurun_out/${tag}_ncu.log 2>&1
 ncu -i $rep.ncu-rep --page raw --csv > /tmp/${tag}_raw.csv 2>/dev/null
 # keep the metrics the roofline / DESIGN tables quote
