@@ -400,6 +400,10 @@ static int run_fwd(const fa_b200_fwd_args& a, FwdMode mode, cudaStream_t stream)
     uint32_t box[4] = {panel, 128, 1, 1};
     if (int rc = make_tmap(which == 0 ? &kp.tm_k : &kp.tm_v, dt, 4, base, dims, str, box)) return rc;
     if (pl.wide) {
+      kp.q_raw = a.q; kp.k_raw = a.k; kp.v_raw = a.v;
+      kp.q_bs = a.q_batch_stride; kp.q_rs = a.q_row_stride; kp.q_hs = a.q_head_stride;
+      kp.k_bs = a.k_batch_stride; kp.k_rs = a.k_row_stride; kp.k_hs = a.k_head_stride;
+      kp.v_bs = a.v_batch_stride; kp.v_rs = a.v_row_stride; kp.v_hs = a.v_head_stride;
       uint32_t box2[4] = {panel, 256, 1, 1};
       if (int rc = make_tmap(which == 0 ? &kp.tm_k256 : &kp.tm_v256, dt, 4, base, dims, str, box2)) return rc;
     }

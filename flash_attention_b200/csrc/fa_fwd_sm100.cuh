@@ -44,6 +44,10 @@ struct FwdKernelParams {
   CUtensorMap tm_v;
   CUtensorMap tm_k256;  // wide-S kernel (fa_fwd_wide_sm100.cuh): the same tensors with a box of 256 rows
   CUtensorMap tm_v256;
+  const void* q_raw;    // wide-S kernel: plain pointers + element strides of q / k / v (its exact per-row fallback reads them)
+  const void* k_raw;
+  const void* v_raw;
+  int64_t q_bs, q_rs, q_hs, k_bs, k_rs, k_hs, v_bs, v_rs, v_hs;
   void* o;
   float* lse;
   float* o_accum;    // (splits, b, h, sq, kD) fp32 when num_splits > 1

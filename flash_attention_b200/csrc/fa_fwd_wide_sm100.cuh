@@ -39,6 +39,13 @@
 #ifndef FA_WIDE_GROUPS
 #define FA_WIDE_GROUPS 2   // measured: 2 groups 1256, 4 groups 1212 TFLOP/s at the C2 shape (profiles/r02_r_wide_4groups_timing.log)
 #endif
+#ifndef FA_WIDE_ONEPASS
+#define FA_WIDE_ONEPASS 0   // 1 (bf16): unmasked block pairs after an item's first take their exponentials against the row maximum of
+                            // the blocks BEFORE them (the groups exchange a block pair's maximum after handing its P over; rows
+                            // whose accumulators could overflow are redone exactly by fwd_wide_slow_row).  Correct (48 tests) but
+                            // slower: 1222 vs 1280 TFLOP/s at the C2 shape -- the row maximum still has to be taken, and taken
+                            // inside the exponential loop it costs more than in front of it (profiles/r02_u_wide_onepass.log)
+#endif
 #ifndef FA_WIDE_DIAG
 #define FA_WIDE_DIAG 0   // TIMING EXPERIMENTS ONLY (wrong results): 1 = exponentials for half of the columns, 3 = every CTA streams the K / V of (batch 0, head 0) (L2-resident)
 #endif
@@ -73,10 +80,48 @@ struct FwdWideCfg {
   static constexpr int kSBar = kSKV + kSlots * kSlotBytes;
   static constexpr int kNumBars = 20;
   static constexpr int kSMisc = kSBar + 8 * kNumBars;     // tmem pointer (4 B), pad, 2 scheduler items
-  static constexpr int kSExch = kSMisc + 32;              // row maxima: uint16 [2 parities][kNG][128]; row sums: float [kNG][128]
+  static constexpr int kSExch = kSMisc + 32;              // 4 slices (one per `warp & 3`) of kNG * 128 bytes: row maxima / row sums
   static constexpr int kSmemBytes = kSExch + 2048;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
+
+// Exact per-row fallback of the one-pass mode (cold: a score more than 2^214 above the row maximum of the blocks before it
+// overflowed the accumulators).  One thread recomputes its query row against keys [col_lo, col_hi) straight from global
+// memory, two passes, fp32, and writes kOC output columns from column oc0 (+ the LSE if write_lse).
+template <typename T, int kOC>
+__device__ __noinline__ void fwd_wide_slow_row(const FwdKernelParams& p, int b, int head, int hk, int qpos, int col_lo, int col_hi,
+                                               int oc0, bool write_lse) {
+  const T* q = reinterpret_cast<const T*>(p.q_raw) + b * p.q_bs + int64_t(qpos) * p.q_rs + int64_t(head) * p.q_hs;
+  const T* kb = reinterpret_cast<const T*>(p.k_raw) + b * p.k_bs + int64_t(hk) * p.k_hs;
+  const T* vb = reinterpret_cast<const T*>(p.v_raw) + b * p.v_bs + int64_t(hk) * p.v_hs;
+  auto dot = [&](int j) {
+    const T* k = kb + int64_t(j) * p.k_rs;
+    float acc = 0.f;
+    for (int c = 0; c < p.d; ++c) acc = fmaf(float(q[c]), float(k[c]), acc);
+    return acc * p.scale;
+  };
+  float m = -INFINITY;
+  for (int j = col_lo; j < col_hi; ++j) m = fmaxf(m, dot(j));
+  float o[kOC];
+#pragma unroll
+  for (int c = 0; c < kOC; ++c) o[c] = 0.f;
+  float l = 0.f;
+  for (int j = col_lo; j < col_hi; ++j) {
+    const float pj = __expf(dot(j) - m);
+    l += pj;
+    const T* v = vb + int64_t(j) * p.v_rs + oc0;
+#pragma unroll
+    for (int c = 0; c < kOC; ++c)
+      if (oc0 + c < p.d) o[c] = fmaf(pj, float(v[c]), o[c]);
+  }
+  const bool dead = !(l > 0.f) || m == -INFINITY;
+  const float inv = dead ? 0.f : 1.0f / l;
+  T* dst = reinterpret_cast<T*>(p.o) + b * p.o_batch_stride + int64_t(qpos) * p.o_row_stride + int64_t(head) * p.o_head_stride + oc0;
+#pragma unroll
+  for (int c = 0; c < kOC; ++c)
+    if (oc0 + c < p.d) dst[c] = T(o[c] * inv);
+  if (write_lse) p.lse[(int64_t(b) * p.h + head) * p.sq + qpos] = dead ? INFINITY : m + __logf(l);
+}
 
 template <typename T, int kNG>
 __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kernel(const __grid_constant__ FwdKernelParams p) {
@@ -85,6 +130,12 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
   constexpr int kC = Cfg::kC, kOC = Cfg::kOC, kW = Cfg::kW;
   constexpr float kNegInf = -INFINITY;
   constexpr float kLagLog2 = 8.0f;
+  // One-pass mode (bf16 only: P needs the exponent range).  P is written as 2^(x - 100), x = (s - m_ref) * scale_log2: the power of
+  // two cancels exactly between O and the row sum, scores within 2^-26 of the reference stay normal bf16 numbers, and a block pair may
+  // exceed the reference (the maximum of the blocks BEFORE it) by up to 2^214 before an accumulator overflows -- rows beyond that are
+  // caught in the epilogue (non-finite row sum) and recomputed exactly by fwd_wide_slow_row.
+  constexpr bool kOnePass = FA_WIDE_ONEPASS && Elt<T>::kFmt == 1;
+  constexpr float kPOffset = kOnePass ? -100.0f : 0.0f;
 
   const int G = int(gridDim.x), cta = int(blockIdx.x);
   const int total_items = p.total_items;
@@ -99,8 +150,9 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t sTmemPtr = smem_base + Cfg::kSMisc;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::kSMisc);
-  uint16_t* exch_max = reinterpret_cast<uint16_t*>(smem_raw + Cfg::kSExch);
-  float* exch_sum = reinterpret_cast<float*>(smem_raw + Cfg::kSExch);
+  // exchange area: one slice of kNG * 128 bytes per group of partner warps (same `warp & 3`: the warps that own the same 32
+  // rows) -- a slice is only ever touched by warps that synchronise on the same named barrier.  Inside a slice the row maxima
+  // (uint16 [2 parities][kNG][32 lanes]) and the row sums of the epilogue (float [kNG][32 lanes]) share the bytes.
 
   FwdSched sched;
   sched.G = G; sched.cta = cta; sched.total = total_items; sched.rounds = rounds; sched.k = 0;
@@ -288,6 +340,8 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
     const uint32_t tS = tmem_base + lane_sel + kC * h;
     const uint32_t tP = tmem_base + lane_sel + 256 + (kC / 2) * h;
     const uint32_t tO = tmem_base + lane_sel + 384 + kOC * h;
+    uint16_t* exch_max = reinterpret_cast<uint16_t*>(smem_raw + Cfg::kSExch + wq * (kNG * 128));
+    float* exch_sum = reinterpret_cast<float*>(smem_raw + Cfg::kSExch + wq * (kNG * 128));
     const uint32_t pbar = 2 + wq;     // named barrier of the kNG warps that own these 32 rows
     auto partner_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(pbar), "n"(32 * kNG) : "memory"); };
     int g = 0;
@@ -308,6 +362,8 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
       if (p.has_left) { int l = qpos + shift - p.wl; col_lo = l > 0 ? l : 0; }
 
       float m_ref = kNegInf, row_sum = 0.f;
+      float mx_pending = kNegInf;   // one-pass mode: row maximum of the last block pair, not yet folded into the reference
+      bool sticky = false;          // one-pass mode: an accumulator of this row may have overflowed
       for (int n = 0; n < N; ++n, ++g) {
         const int col0 = (p_hi - 1 - n) * 256 + kC * h;
         mbar_wait(bar(S_FULL), g & 1, 300 + h);
@@ -316,17 +372,36 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
         tc_fence_after();
         uint32_t su[kC];
         float* s = reinterpret_cast<float*>(su);
+        // masks: warp-uniform per group; a block pair is one-pass only if NO group has to mask (uniform across the partners)
         bool need_mask = col0 + kC > sk_b;
         if (p.has_right) need_mask |= col0 + kC > t_qlo + 1 + shift + p.wr;
         if (p.has_left) need_mask |= col0 < t_qhi + shift - p.wl;
+        bool any_mask;
+        {
+          const int pc0 = (p_hi - 1 - n) * 256;
+          any_mask = pc0 + 256 > sk_b;
+          if (p.has_right) any_mask |= pc0 + 256 > t_qlo + 1 + shift + p.wr;
+          if (p.has_left) any_mask |= pc0 < t_qhi + shift - p.wl;
+        }
+        // ... and only once every row of the warp has a finite reference (a row's first visible block pair is two-pass: against
+        // "reference 0" strongly negative scores would underflow).  Same answer in every partner: same m_ref / mx_pending.
+        const bool have_ref = fmaxf(m_ref, mx_pending) != kNegInf;
+        const bool onepass = kOnePass && n > 0 && !any_mask && __all_sync(0xffffffffu, have_ref);
 #pragma unroll
         for (int c = 0; c < kC / 2; c += 32) tmem_ld_x32(tS + c, su + c);
         tmem_wait_ld();
         WTS(ts_on, n, 5 + 6 * h);
 #pragma unroll
-        for (int c = kC / 2; c < kC; c += 32) tmem_ld_x32(tS + c, su + c);   // streams out of TMEM while the first half is reduced
-        float mx;
-        if (!need_mask) {
+        for (int c = kC / 2; c < kC; c += 32) tmem_ld_x32(tS + c, su + c);   // streams out of TMEM while the first half is worked on
+        float mx = kNegInf;
+        if (onepass) {
+          // the reference moves to the maximum of the blocks before this one (exchanged after the previous hand-over)
+          mx = mx_pending;
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(S_READ));
+        } else if (!need_mask) {
           float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]);
           float m2 = fmax3(s[6], s[7], s[8]), m3 = fmax3(s[9], s[10], s[11]);
 #pragma unroll
@@ -366,21 +441,24 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
           }
           mx = fmax3(m0, m1, fmaxf(s[kC - 2], s[kC - 1]));
         }
-        // ---- the kNG warps that own these 32 rows agree on the row maximum of the whole block pair.  The maxima travel as
+        // ---- the kNG warps that own these 32 rows agree on the row maximum of a block pair.  The maxima travel as
         // bf16 rounded UP (a reference slightly above the true maximum is as good as the maximum itself, and every partner
         // sees the same kNG numbers, its own included), two parities deep: one named barrier per block pair is enough.
-        WTS(ts_on, n, 6 + 6 * h);
-        {
-          uint16_t* ex = exch_max + (g & 1) * (kNG * 128);
-          const uint32_t bits = __float_as_uint(mx);
-          ex[h * 128 + trow] = uint16_t((mx >= 0.f ? bits + 0xFFFFu : bits) >> 16);
+        // Two-pass block pairs exchange BEFORE the exponentials, one-pass block pairs AFTER the hand-over of P (below).
+        auto exchange = [&](float mine) {
+          uint16_t* ex = exch_max + (g & 1) * (kNG * 32);
+          const uint32_t bits = __float_as_uint(mine);
+          ex[h * 32 + lane] = uint16_t((mine >= 0.f ? bits + 0xFFFFu : bits) >> 16);
           partner_sync();
-          uint32_t mb = 0xFF80u;   // -inf
           float mr = kNegInf;
 #pragma unroll
-          for (int i = 0; i < kNG; ++i) mr = fmaxf(mr, __uint_as_float(uint32_t(ex[i * 128 + trow]) << 16));
-          (void)mb;
-          mx = mr;
+          for (int i = 0; i < kNG; ++i) mr = fmaxf(mr, __uint_as_float(uint32_t(ex[i * 32 + lane]) << 16));
+          return mr;
+        };
+        WTS(ts_on, n, 6 + 6 * h);
+        if (!onepass) {
+          mx = fmaxf(exchange(mx), mx_pending);   // (a one-pass block pair before this one may have left its maximum pending)
+          mx_pending = kNegInf;
         }
         WTS(ts_on, n, 7 + 6 * h);
         // ---- online softmax with a lazily updated reference (all groups take identical decisions: same inputs)
@@ -396,14 +474,16 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
           if (__any_sync(0xffffffffu, need)) {
             mbar_wait(bar(PV_DONE), (g - 1) & 1, 310 + h);   // P V of the previous block pair has landed
             tc_fence_after();
-            const float f = need ? ex2((m_ref - m_new) * scale_log2) : 1.0f;
+            // The factor is applied in two halves: in one-pass mode O may hold numbers as large as 2^114 that a reference jump of
+            // 2^200 brings back to 2^-86 -- the product is representable, 2^-200 itself is not (flushed to zero).
+            const float f = need ? ex2(0.5f * (m_ref - m_new) * scale_log2) : 1.0f;
 #pragma unroll
             for (int cc = 0; cc < kOC; cc += 32) {   // this group's share of the O columns
               uint32_t o[32];
               tmem_ld_x32(tO + cc, o);
               tmem_wait_ld();
 #pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint((__uint_as_float(o[c]) * f) * f);
               tmem_st_x32(tO + cc, o);
             }
             tmem_wait_st();
@@ -411,21 +491,30 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
             // every share of the O rows must be rescaled before ANY group hands its P to the MMA thread (the first P V step
             // accumulates into all 128 columns)
             partner_sync();
-            row_sum *= f;
+            row_sum = (row_sum * f) * f;
             if (need) m_ref = m_new;
           }
         }
-        const float neg_ms = (m_ref == kNegInf) ? 0.f : -m_ref * scale_log2;
+        const float neg_ms = (m_ref == kNegInf) ? kPOffset : kPOffset - m_ref * scale_log2;
         // ---- P = exp2(S * scale_log2 - m * scale_log2): software-pipelined as in fa_fwd_sm100.cuh (scaling of chunk k+1
         // made to depend on an exponential of chunk k-1, so that MUFU and FMA pipes run side by side); the packed words
-        // stay in registers (they replace the scores they came from) until the P buffer is free.
+        // stay in registers (they replace the scores they came from) until the P buffer is free.  One-pass block pairs pick
+        // up their own row maximum on the way (raw scores, before the scaling).
         const uint64_t sc2 = pack2(scale_log2, scale_log2);
         const uint64_t ng2 = pack2(neg_ms, neg_ms);
         const uint64_t zero2 = pack2(0.f, 0.f);
         uint64_t acc_a = zero2, acc_b = zero2;
         uint32_t pk[kC / 2];
         uint64_t tok_prev = zero2, tok_cur = zero2;
+        float lm0 = kNegInf, lm1 = kNegInf;
         auto stage_a = [&](int k, uint64_t sc) {
+          if constexpr (kOnePass) {   // (unconditional: a branch here would cut the software pipeline into basic blocks)
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+              lm0 = fmax3(lm0, s[16 * k + c], s[16 * k + c + 1]);
+              lm1 = fmax3(lm1, s[16 * k + c + 2], s[16 * k + c + 3]);
+            }
+          }
 #pragma unroll
           for (int c = 0; c < 16; c += 2)
             unpack2(fma2(pack2(s[16 * k + c], s[16 * k + c + 1]), sc, ng2), s[16 * k + c], s[16 * k + c + 1]);
@@ -456,7 +545,12 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
             else acc_a = add2(acc_a, e2);
             if (c == 10) {
               tok_prev = tok_cur;
-              tok_cur = e2;
+              if constexpr (kOnePass) {   // (an exponential against a lagging reference may be inf: inf * 0 would poison the scale)
+                const float tk = fminf(e0, 1.0f);
+                tok_cur = pack2(tk, tk);
+              } else {
+                tok_cur = e2;
+              }
             }
             pk[col / 2] = Elt<T>::pack(e0, e1);
           }
@@ -475,23 +569,32 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
           float a0, a1, b0, b1;
           unpack2(acc_a, a0, a1);
           unpack2(acc_b, b0, b1);
-          row_sum += (a0 + a1) + (b0 + b1);
+          const float bsum = (a0 + a1) + (b0 + b1);
+          if constexpr (kOnePass) sticky |= !(bsum <= 1.0e18f);   // a score > 2^160 above the lagging reference: the row is redone exactly
+          row_sum += bsum;
+        }
+        if (onepass) {
+          const float lm = fmaxf(lm0, lm1);
+          // (the polynomial exp2 wraps around above 2^127 instead of returning inf: watch the largest exponent itself)
+          sticky |= fmaf(lm, scale_log2, neg_ms) > 60.0f;
+          mx_pending = exchange(lm);   // off the S -> P chain; applied at the next block pair
         }
       }
 
       // ---------------------------------------------------------------- epilogue: join the row sums, write this group's O columns
       partner_sync();   // (the sums reuse the buffer of the maxima: every partner has read the last block pair's)
-      exch_sum[h * 128 + trow] = row_sum;
+      if (sticky) row_sum = INFINITY;   // every partner then sees a non-finite joined sum
+      exch_sum[h * 32 + lane] = row_sum;
       partner_sync();
       row_sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < kNG; ++i) row_sum += exch_sum[i * 128 + trow];
+      for (int i = 0; i < kNG; ++i) row_sum += exch_sum[i * 32 + lane];
       partner_sync();   // (the next item's first exchange reuses the buffer)
       float inv = 0.f, lse_val;
       const bool dead = m_ref == kNegInf || !(row_sum > 0.f);
       if (!dead) {
         inv = 1.0f / row_sum;
-        lse_val = m_ref * p.scale + __logf(row_sum);
+        lse_val = m_ref * p.scale + __logf(row_sum) - kPOffset * 0.6931471805599453f;
       } else {
         lse_val = INFINITY;   // fully masked row (softmax.h:180)
       }
@@ -506,7 +609,11 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(O_FREE));
       }
-      if (row_valid) {
+      bool overflowed = false;
+      if constexpr (kOnePass) overflowed = !(row_sum <= 1.0e18f);   // inf, NaN or absurd: the same joined sum in every partner
+      if (overflowed) {
+        if (row_valid) fwd_wide_slow_row<T, kOC>(p, bidb, head, w.hk_idx, qpos, col_lo, col_hi, kOC * h, h == 0);
+      } else if (row_valid) {
         T* dst = reinterpret_cast<T*>(p.o) + bidb * p.o_batch_stride + int64_t(qpos) * p.o_row_stride +
                  int64_t(head) * p.o_head_stride + kOC * h;
 #pragma unroll

@@ -86,3 +86,50 @@ def test_matches_two_tile_kernel_at_baseline_slice(fab, monkeypatch):
     out_t, lse_t, _ = fab.flash_attn_func(q, k, v, return_attn_probs=True)
     assert (out_w.float() - out_t.float()).abs().max().item() <= 2e-3
     assert (lse_w - lse_t).abs().max().item() <= 1e-4
+
+
+# ---- one-pass block pairs (exponentials against the row maximum of the blocks BEFORE the pair; fa_fwd_wide_sm100.cuh)
+@pytest.mark.parametrize("kval,col", [(300.0, 13), (300.0, 700), (450.0, 200), (700.0, 5), (700.0, 1000), (1500.0, 333)])
+def test_onepass_huge_jumps(fab, kval, col):
+    # every query shares a component with ONE key, whose score is 4 * kval / sqrt(128) nats above the rest: 153 / 230 / 357 /
+    # 765 in the exp2 domain -- below, inside and beyond the range the lagging reference can absorb (2^214): the last ones
+    # overflow an accumulator and go through the exact per-row fallback
+    b, s, h, d = 1, 1536, 2, 128
+    q, k, v = make_qkv(b, s, s, h, h, d)
+    q = q.clone(); k = k.clone()
+    q[..., 0] = 4.0
+    k[:, col, :, 0] = kval
+    if kval > 400.0:
+        _run(fab, q, k, v)      # exact fallback: the reference's rule holds even for these one-hot rows (the bound is ~1e-7)
+        return
+    # Below the fallback's range a one-pass block pair keeps the reference it came with, so the dominant probability is
+    # bf16(2^frac) instead of exactly 1 (as after any lazy rescale, here for jumps of any size): at most one bf16 ulp of O on
+    # (near-)one-hot rows.  The reference's rule degenerates to atol = 1e-7 on such rows (its low-precision oracle is exact).
+    from tests.util import fwd_tolerances
+
+    out, lse, _ = fab.flash_attn_func(q, k, v, return_attn_probs=True)
+    ref32, lse_ref, bound = fwd_tolerances(q, k, v)
+    err = (out.float().cpu() - ref32).abs()
+    assert not torch.isnan(out).any()
+    assert (err <= torch.clamp(ref32.abs() * 2.0 ** -7, min=max(bound, 1e-6))).all(), f"max err {err.max().item():.3e}"
+    assert (lse.float().cpu() - lse_ref).abs().max().item() <= 2e-3 * lse_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_onepass_strongly_negative_scores(fab, causal):
+    # every score is ~ -250 nats: a reference of 0 would underflow every exponential
+    b, s, h, d = 1, 1280, 2, 128
+    q, k, v = make_qkv(b, s, s, h, h, d)
+    q = q.clone(); k = k.clone()
+    q[..., 1] = 50.0
+    k[..., 1] = -56.0
+    _run(fab, q, k, v, causal=causal)
+
+
+def test_onepass_steady_drift(fab):
+    # every earlier key block scores higher than the later ones: the lagging reference moves at every block pair
+    b, s, h, d = 2, 4096, 2, 128
+    q, k, v = make_qkv(b, s, s, h, h, d)
+    ramp = torch.linspace(6.0, 0.2, s, device="cuda").view(1, s, 1, 1)
+    k = (k.float() * ramp).to(torch.bfloat16)
+    _run(fab, q, k, v, causal=True)
