@@ -103,6 +103,7 @@ SYMBOLS = {
     "fa_b200_mha_fwd_kvcache": (C.c_int, [C.POINTER(FwdArgs), _vp]),
     "fa_b200_fwd_workspace_bytes": (_sz, [C.POINTER(FwdArgs)]),
     "fa_b200_fwd_num_splits": (C.c_int, [C.POINTER(FwdArgs)]),
+    "fa_b200_fwd_kernel_kind": (C.c_int, [C.POINTER(FwdArgs)]),
     "fa_b200_fwd_plan": (C.c_int, [C.POINTER(FwdArgs), C.POINTER(C.c_int32)]),
     "fa_b200_mha_bwd": (C.c_int, [C.POINTER(BwdArgs), _vp]),
     "fa_b200_mha_varlen_bwd": (C.c_int, [C.POINTER(BwdArgs), _vp]),

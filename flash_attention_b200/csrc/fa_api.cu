@@ -600,6 +600,12 @@ int fa_b200_fwd_plan(const fa_b200_fwd_args* args, int32_t out[3]) {
   return 0;
 }
 
+int fa_b200_fwd_kernel_kind(const fa_b200_fwd_args* args) {
+  FwdPlan pl;
+  if (!args || plan_fwd(*args, mode_of(args), &pl)) return -1;
+  return pl.wide ? 3 : pl.tiles;
+}
+
 int fa_b200_fwd_num_splits(const fa_b200_fwd_args* args) {
   FwdPlan pl;
   if (!args || plan_fwd(*args, mode_of(args), &pl)) return -1;

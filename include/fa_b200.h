@@ -149,6 +149,11 @@ size_t fa_b200_fwd_workspace_bytes(const fa_b200_fwd_args* args);
 int fa_b200_fwd_num_splits(const fa_b200_fwd_args* args);
 /* the full plan: out[0] = num_splits, out[1] = GQA pack factor, out[2] = number of 256-row m-blocks (FA3 get_scheduler_metadata) */
 int fa_b200_fwd_plan(const fa_b200_fwd_args* args, int32_t out[3]);
+/* which forward kernel the call will launch: 1 = one query tile per CTA (two CTAs per SM: decode, short items),
+ * 2 = two query tiles per CTA (the throughput configuration), 3 = the wide-S kernel (S = Q K^T 256 keys per
+ * instruction; dense fp16 / bf16, head dim <= 128, no dropout / softcap / ALiBi / split-KV; opt-in: FA_B200_FWD_WIDE=1);
+ * negative on an argument error.  (The reference picks its kernel inside run_mha_fwd, flash_api.cpp:243-279.) */
+int fa_b200_fwd_kernel_kind(const fa_b200_fwd_args* args);
 
 /* ---- backward ---- */
 int fa_b200_mha_bwd(const fa_b200_bwd_args* args, fa_b200_stream_t stream);

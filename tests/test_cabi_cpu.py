@@ -102,6 +102,37 @@ def test_forward_plan_host_logic(fa_lib):
     assert splits > 1
 
 
+def test_forward_kernel_choice(fa_lib, monkeypatch):
+    """Which forward kernel a dense call takes (host-only): the wide-S kernel is opt-in and only for what it supports."""
+    fa_lib.fa_b200_fwd_kernel_kind.restype = C.c_int
+
+    def kind(**kw):
+        a = _lib.FwdArgs()
+        a.dtype = _lib.BF16
+        a.q = a.k = a.v = a.out = a.softmax_lse = 16
+        a.b, a.seqlen_q, a.seqlen_k, a.h, a.h_k, a.d = 4, 8192, 8192, 16, 16, 128
+        a.window_size_left = a.window_size_right = -1
+        a.softmax_scale = 0.088
+        for k_, v_ in kw.items():
+            setattr(a, k_, v_)
+        return fa_lib.fa_b200_fwd_kernel_kind(C.byref(a))
+
+    monkeypatch.delenv("FA_B200_FWD_WIDE", raising=False)
+    assert kind() == 2                                   # long non-causal stream: two query tiles per CTA
+    assert kind(seqlen_q=1024, seqlen_k=1024, is_causal=1) == 1   # short causal items: two CTAs per SM
+    monkeypatch.setenv("FA_B200_FWD_WIDE", "1")
+    assert kind() == 3
+    assert kind(is_causal=1) == 3
+    assert kind(d=96) == 3
+    assert kind(d=64) == 2                               # head dim 64 has its own configuration
+    assert kind(p_dropout=0.1) == 1                      # dropout kernels are one-tile
+    assert kind(softcap=30.0) == 2
+    assert kind(dtype=_lib.FP8_E4M3) == 2
+    assert kind(seqlen_q=128) != 3                       # a single query tile: nothing to stream against
+    assert kind(num_splits=4) != 3
+    assert kind(d=100) == -1                             # argument errors come back negative
+
+
 def test_dropout_and_backward_argument_checks_without_gpu(fa_lib):
     """Host-side validation added with dropout / the pair backward: all of it runs before any CUDA call."""
     a = _lib.FwdArgs()
