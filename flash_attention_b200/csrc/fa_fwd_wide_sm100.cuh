@@ -150,9 +150,10 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t sTmemPtr = smem_base + Cfg::kSMisc;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::kSMisc);
-  // exchange area: one slice of kNG * 128 bytes per group of partner warps (same `warp & 3`: the warps that own the same 32
+  // exchange area: one slice of 512 bytes per group of partner warps (same `warp & 3`: the warps that own the same 32
   // rows) -- a slice is only ever touched by warps that synchronise on the same named barrier.  Inside a slice the row maxima
-  // (uint16 [2 parities][kNG][32 lanes]) and the row sums of the epilogue (float [kNG][32 lanes]) share the bytes.
+  // ([2 parities][kNG][32 lanes]: fp32 for two groups, bf16 for four) and the row sums of the epilogue (float [kNG][32 lanes])
+  // share the bytes.
 
   FwdSched sched;
   sched.G = G; sched.cta = cta; sched.total = total_items; sched.rounds = rounds; sched.k = 0;
@@ -340,8 +341,8 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
     const uint32_t tS = tmem_base + lane_sel + kC * h;
     const uint32_t tP = tmem_base + lane_sel + 256 + (kC / 2) * h;
     const uint32_t tO = tmem_base + lane_sel + 384 + kOC * h;
-    uint16_t* exch_max = reinterpret_cast<uint16_t*>(smem_raw + Cfg::kSExch + wq * (kNG * 128));
-    float* exch_sum = reinterpret_cast<float*>(smem_raw + Cfg::kSExch + wq * (kNG * 128));
+    uint8_t* exch_slice = smem_raw + Cfg::kSExch + wq * 512;
+    float* exch_sum = reinterpret_cast<float*>(exch_slice);
     const uint32_t pbar = 2 + wq;     // named barrier of the kNG warps that own these 32 rows
     auto partner_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(pbar), "n"(32 * kNG) : "memory"); };
     int g = 0;
@@ -441,18 +442,25 @@ __global__ void __launch_bounds__(FwdWideCfg<kNG>::kThreads, 1) fa_fwd_wide_kern
           }
           mx = fmax3(m0, m1, fmaxf(s[kC - 2], s[kC - 1]));
         }
-        // ---- the kNG warps that own these 32 rows agree on the row maximum of a block pair.  The maxima travel as
-        // bf16 rounded UP (a reference slightly above the true maximum is as good as the maximum itself, and every partner
-        // sees the same kNG numbers, its own included), two parities deep: one named barrier per block pair is enough.
+        // ---- the kNG warps that own these 32 rows agree on the row maximum of a block pair through their slice of the exchange
+        // area, two parities deep: one named barrier per block pair is enough.
         // Two-pass block pairs exchange BEFORE the exponentials, one-pass block pairs AFTER the hand-over of P (below).
         auto exchange = [&](float mine) {
-          uint16_t* ex = exch_max + (g & 1) * (kNG * 32);
-          const uint32_t bits = __float_as_uint(mine);
-          ex[h * 32 + lane] = uint16_t((mine >= 0.f ? bits + 0xFFFFu : bits) >> 16);
-          partner_sync();
           float mr = kNegInf;
+          if constexpr (kNG == 2) {   // exact maxima: the reference of a two-pass block pair IS its row maximum (P of it = 1)
+            float* ex = reinterpret_cast<float*>(exch_slice) + (g & 1) * (kNG * 32);
+            ex[h * 32 + lane] = mine;
+            partner_sync();
 #pragma unroll
-          for (int i = 0; i < kNG; ++i) mr = fmaxf(mr, __uint_as_float(uint32_t(ex[i * 32 + lane]) << 16));
+            for (int i = 0; i < kNG; ++i) mr = fmaxf(mr, ex[i * 32 + lane]);
+          } else {                    // four groups: 512 bytes per slice only hold bf16, rounded UP (a reference slightly above the
+            uint16_t* ex = reinterpret_cast<uint16_t*>(exch_slice) + (g & 1) * (kNG * 32);   // maximum is still a valid reference)
+            const uint32_t bits = __float_as_uint(mine);
+            ex[h * 32 + lane] = uint16_t((mine >= 0.f ? bits + 0xFFFFu : bits) >> 16);
+            partner_sync();
+#pragma unroll
+            for (int i = 0; i < kNG; ++i) mr = fmaxf(mr, __uint_as_float(uint32_t(ex[i * 32 + lane]) << 16));
+          }
           return mr;
         };
         WTS(ts_on, n, 6 + 6 * h);
