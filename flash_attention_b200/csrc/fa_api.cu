@@ -231,8 +231,10 @@ static int plan_fwd(const fa_b200_fwd_args& a, FwdMode mode, FwdPlan* pl) {
     // (est_blocks <= 64), non-causal only up to s = 1k (est_blocks <= 8)
     // round 2: with the persistent loop (prologue / epilogue overlapped, per-tile block ranges) the 2-tile kernel also
     // wins on long causal problems; FA_B200_FWD_TILE_LIMIT_CAUSAL overrides the crossover for experiments
-    static const int causal_limit = [] { const char* e = getenv("FA_B200_FWD_TILE_LIMIT_CAUSAL"); return e ? atoi(e) : 8; }();
-    const int limit = pl->has_right ? causal_limit : 8;
+    // round 2, final build (profiles/r02_z_short_knobs.log): the crossover sits lower than that -- at 8 blocks per item the 2-tile
+    // kernel is 5 % faster both non-causal (s = 1024: 933 vs 889 TFLOP/s) and causal (s = 2048: 835 vs 793); at 4 they are equal
+    static const int causal_limit = [] { const char* e = getenv("FA_B200_FWD_TILE_LIMIT_CAUSAL"); return e ? atoi(e) : 4; }();
+    const int limit = pl->has_right ? causal_limit : 4;
     pl->tiles = (a.seqlen_q * (g > 1 && is_pow2(g) ? g : 1) <= 128 || est_blocks <= limit) ? 1 : 2;
     if (const char* e = getenv("FA_B200_FWD_TILES")) { if (e[0] == '1') pl->tiles = 1; if (e[0] == '2') pl->tiles = 2; }
     if (pl->kD == 256) pl->tiles = 1;  // S (128) + O (256) TMEM columns: one tile per CTA (forward only)
